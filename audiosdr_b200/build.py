@@ -1,0 +1,54 @@
+"""audiosdr_b200/build.py -- compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsdr_batch.so")
+SOURCES = ["sdr_kernel.cu", "sdr_host.cpp"]
+DEPS = SOURCES + ["sdr_pipeline.cuh", "sdr_types.h", "sdr_kernel.h", "sdr_tables.inc", os.path.join("..", "..", "include", "sdr_batch.h")]
+
+# -fmad=false: the reference rounds every product and every sum separately (x86-64 SSE, no FMA); contraction
+# would change low bits and, through the blanker/AGC/PLL thresholds, whole decisions.  Division and square root
+# stay IEEE (nvcc defaults), denormals are kept (no -ftz).
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-prec-div=true",
+              "-prec-sqrt=true", "-ftz=false", "--extended-lambda", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+              "-diag-suppress", "186"]
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build_library(force=False, verbose=False):
+    """Builds audiosdr_b200/libsdr_batch.so; returns its path."""
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, s) if not s.endswith(".cpp") else os.path.join(CSRC, s) for s in SOURCES]
+    # sdr_host.cpp is plain C++ that calls the CUDA runtime: compile it as CUDA so that one nvcc call links everything
+    cmd = [c for c in cmd]
+    idx = cmd.index(os.path.join(CSRC, "sdr_host.cpp"))
+    cmd[idx:idx + 1] = ["-x", "cu", os.path.join(CSRC, "sdr_host.cpp")]
+    idxk = cmd.index(os.path.join(CSRC, "sdr_kernel.cu"))
+    cmd[idxk:idxk + 1] = ["-x", "cu", os.path.join(CSRC, "sdr_kernel.cu")]
+    cmd += ["-o", LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,583 @@
+/* sdr_host.cpp -- host side of the C ABI (include/sdr_batch.h).
+ *
+ * Keeps, per channel, a shadow of the reference object's CONFIGURATION members and replays the
+ * reference's setter semantics on it (which setter rebuilds which constant, which one re-initialises
+ * which state: SURVEY 8a13, Q5, Q7), resolves it into the device-side SdrChanCfg with the same host
+ * expressions the reference uses (so the constants are bit-equal), groups channels by
+ * pipeline class into 32-lane groups, and launches the kernels.  No signal arithmetic happens here.
+ *
+ * C: = reference SRC/AudioSDRlib/AudioSDR.cpp, H: = .../AudioSDR.h.
+ *
+ * Built twice: with nvcc into the product library (CUDA backend), and with -DSDR_EMU by the test
+ * suite (tests/emu) where "device" memory is host memory and the launch runs the role bodies of
+ * sdr_pipeline.cuh lane by lane -- a logic check that needs no GPU, never shipped.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sdr_batch.h"
+#include "sdr_kernel.h"
+#include "sdr_tables.inc"
+#include "sdr_types.h"
+
+#ifndef SDR_EMU
+#include <cuda_runtime.h>
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+/* ------------------------------------------------------------------ backend */
+#ifndef SDR_EMU
+#define CU(call)                                                                           \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) return fail(SDR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+int dev_alloc(void **p, size_t n) { CU(cudaMalloc(p, n)); return 0; }
+void dev_free(void *p) { if (p) cudaFree(p); }
+int dev_zero(void *p, size_t n, void *s) { CU(cudaMemsetAsync(p, 0, n, (cudaStream_t)s)); return 0; }
+int h2d(void *d, const void *h, size_t n, void *s) { CU(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)s)); return 0; }
+int d2h(void *h, const void *d, size_t n, void *s) { CU(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)s)); return 0; }
+int h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t w, size_t rows, void *s) {
+  CU(cudaMemcpy2DAsync(d, dp, h, hp, w, rows, cudaMemcpyHostToDevice, (cudaStream_t)s)); return 0;
+}
+int d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t w, size_t rows, void *s) {
+  CU(cudaMemcpy2DAsync(h, hp, d, dp, w, rows, cudaMemcpyDeviceToHost, (cudaStream_t)s)); return 0;
+}
+int dev_sync(void *s) { CU(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
+int dev_select(int dev) { CU(cudaSetDevice(dev)); return 0; }
+#else
+int dev_alloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : fail(SDR_ERR_NOMEM, "calloc"); }
+void dev_free(void *p) { free(p); }
+int dev_zero(void *p, size_t n, void *) { memset(p, 0, n); return 0; }
+int h2d(void *d, const void *h, size_t n, void *) { memcpy(d, h, n); return 0; }
+int d2h(void *h, const void *d, size_t n, void *) { memcpy(h, d, n); return 0; }
+int h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t w, size_t rows, void *) {
+  for (size_t r = 0; r < rows; r++) memcpy((char *)d + r * dp, (const char *)h + r * hp, w); return 0;
+}
+int d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t w, size_t rows, void *) {
+  for (size_t r = 0; r < rows; r++) memcpy((char *)h + r * hp, (const char *)d + r * dp, w); return 0;
+}
+int dev_sync(void *) { return 0; }
+int dev_select(int) { return 0; }
+#endif
+
+inline float tabf(const uint32_t *t, int i) { float f; memcpy(&f, &t[i], 4); return f; }
+
+const float FS = SDR_SAMPLE_RATE;
+const double PI_D = 3.1415926535897932384626433832795; /* Arduino PI */
+const float IF_CENTER = 6890.0f, BW_SSB = 3000.0f, BW_CW = 1000.0f, BW_WSPR = 1000.0f, BW_AM = 8500.0f; /* H:164-168 */
+
+/* ------------------------------------------------------------------ per-channel shadow of the reference's configuration */
+struct Shadow {
+  int mode; float freq_shift; bool muted;
+  float in_gain, in_gain_i, in_gain_q, gain_balance, out_gain;
+  bool aud_on; int aud_id; int aud_set; int if_set;
+  int als_m, als_delay; float als_lambda; bool als_on, als_notch, als_adapt;
+  float thr, slope, knee, t_att, t_rel, t_hang, a_att, b_att, a_rel, b_rel, static_gain; uint32_t hang_count; bool agc_on;
+  int lut_id;
+  float nb_thr; bool nb_on;
+};
+
+struct AgcKey {
+  uint32_t a, b, c;
+  bool operator<(const AgcKey &o) const { return a != o.a ? a < o.a : (b != o.b ? b < o.b : c < o.c); }
+};
+inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+/* H:483-491 */
+float log2_approx(float v) {
+  int e; float m = frexpf(fabsf(v), &e);
+  return (((1.23149591368684f * m - 4.11852516267426f) * m + 6.02197014179219f) * m - 3.13396450166353f) + e;
+}
+/* agc_createLookupTable, C:459-480.  130 entries are computed (the reference writes one past its
+ * 129-float array); the hot path reads entries 0..128 only. */
+void build_agc_lut(float thr, float slope, float knee, float *lut) {
+  float lo = expf(2.3025 * (thr - knee / 2.0) / 20.0);
+  float hi = expf(2.3025 * (thr + knee / 2.0) / 20.0);
+  for (int i = 0; i < 130; i++) {
+    float in = (float)i / 128.0;
+    float in_db = 6.026 * log2_approx(in);
+    if (in < lo) lut[i] = 1.0;
+    else if (in > hi) { float out_db = (thr + (in_db - thr) * slope); lut[i] = expf(2.3025 * (out_db - in_db) / 20.0); }
+    else {
+      float out_db = in_db + ((slope - 1.0) * (in_db - thr + knee / 2.0) * (in_db - thr + knee / 2.0)) / (2.0 * knee);
+      lut[i] = expf(2.3025 * (out_db - in_db) / 20.0);
+    }
+  }
+  lut[130] = lut[131] = 0.0f;
+}
+
+}  // namespace
+
+struct sdr_batch {
+  sdr_batch_desc desc;
+  uint32_t n_ch; size_t ch_stride;
+  std::vector<Shadow> sh;
+  std::vector<uint32_t> pend_reset; /* per channel SDRK_R_* bits to replay before the next block */
+  std::vector<uint32_t> dirty_list;
+  bool cfg_dirty, groups_dirty, luts_dirty;
+  std::map<AgcKey, int> lut_index;
+  std::vector<float> luts; /* [n][SDR_AGC_LUT_STRIDE] */
+  /* device */
+  float *d_state; SdrChanCfg *d_cfg; SdrGroup *d_groups; float *d_luts; SdrTables *d_tabs;
+  uint32_t *d_reset_ch, *d_reset_mask; size_t reset_cap; size_t luts_cap; size_t groups_cap;
+  float *d_gather; uint32_t *d_gather_ids; uint32_t *d_gather_words; size_t gather_cap;
+  void *d_in_i, *d_in_q, *d_out; size_t stage_in_bytes, stage_out_bytes;
+  uint32_t n_groups;
+  uint64_t blocks_done, launches;
+  void *last_stream;
+  std::vector<SdrChanCfg> h_cfg;
+  std::vector<SdrGroup> h_groups;
+};
+
+namespace {
+
+int lut_for(sdr_batch *h, float thr, float slope, float knee) {
+  AgcKey k{fbits(thr), fbits(slope), fbits(knee)};
+  auto it = h->lut_index.find(k);
+  if (it != h->lut_index.end()) return it->second;
+  int id = (int)(h->luts.size() / SDR_AGC_LUT_STRIDE);
+  h->luts.resize(h->luts.size() + SDR_AGC_LUT_STRIDE);
+  build_agc_lut(thr, slope, knee, &h->luts[(size_t)id * SDR_AGC_LUT_STRIDE]);
+  h->lut_index[k] = id;
+  h->luts_dirty = true;
+  return id;
+}
+
+/* setDemodMode, C:187-222: sets _freq_shift and re-initialises BOTH IF cascades (state zeroed); nothing else */
+int set_mode(sdr_batch *h, uint32_t c, int m) {
+  Shadow &s = h->sh[c];
+  if (m < 0 || m > 6) return fail(SDR_ERR_MODE, "setDemodMode: mode outside 0..6");
+  int old_cls = (s.mode == SDR_AM || s.mode == SDR_SAM) ? CLS_ENV : CLS_SSB;
+  s.mode = m;
+  if (m == SDR_USB) { s.freq_shift = IF_CENTER - BW_SSB / 2.0; s.if_set = 0; }
+  else if (m == SDR_LSB) { s.freq_shift = IF_CENTER + BW_SSB / 2.0; s.if_set = 0; }
+  else if (m == SDR_WSPR) { s.freq_shift = IF_CENTER - BW_SSB / 2.0; s.if_set = 2; }
+  else if (m == SDR_CW_USB) { s.freq_shift = IF_CENTER - BW_CW / 2.0; s.if_set = 1; }
+  else if (m == SDR_CW_LSB) { s.freq_shift = IF_CENTER + BW_CW / 2.0; s.if_set = 1; }
+  else { s.freq_shift = IF_CENTER; s.if_set = 3; }
+  h->pend_reset[c] |= SDRK_R_IF;
+  int cls = (m == SDR_AM || m == SDR_SAM) ? CLS_ENV : CLS_SSB;
+  if (cls != old_cls) h->groups_dirty = true;
+  return 0;
+}
+
+void agc_attack(Shadow &s, float ms) { s.t_att = ms; s.a_att = exp(log(0.1) / (FS * s.t_att / 1000.0)); s.b_att = 1.0 - s.a_att; }   /* C:551-555 */
+void agc_release(Shadow &s, float ms) { s.t_rel = ms; s.a_rel = exp(log(0.1) / (FS * s.t_rel / 1000.0)); s.b_rel = 1.0 - s.a_rel; } /* C:557-561 */
+void agc_hang(Shadow &s, float ms) { s.t_hang = ms; s.hang_count = s.t_hang * FS / 1000.0; }                                         /* C:563-566 */
+
+/* init(), C:174-185 */
+void do_init(sdr_batch *h, uint32_t c) {
+  Shadow &s = h->sh[c];
+  s.aud_set = SDR_AUDIO_2700;
+  /* agc_init, C:439-457 */
+  s.thr = -60.0; s.slope = 0.1; s.knee = 2.0; s.t_att = 5.0; s.t_rel = 500.0; s.t_hang = 100.0;
+  s.hang_count = FS * (s.t_hang / 1000.0);
+  s.a_att = exp(log(0.1) / (FS * s.t_att / 1000.0)); s.b_att = 1.0 - s.a_att;
+  s.a_rel = exp(log(0.1) / (FS * s.t_rel / 1000.0)); s.b_rel = 1.0 - s.a_rel;
+  s.agc_on = true;
+  s.lut_id = lut_for(h, s.thr, s.slope, s.knee);
+  h->pend_reset[c] |= SDRK_R_AUD | SDRK_R_IF | SDRK_R_IMG | SDRK_R_NB;
+  set_mode(h, c, SDR_LSB);
+  s.muted = false;
+}
+
+/* constructor defaults, H:164-284 (members never initialised there read as zero) */
+void construct(sdr_batch *h, uint32_t c) {
+  Shadow &s = h->sh[c];
+  memset(&s, 0, sizeof s);
+  s.in_gain = s.in_gain_i = s.in_gain_q = s.gain_balance = 1.0f; s.out_gain = 0.5; s.muted = true;
+  s.als_m = 55; s.als_delay = 3; s.als_lambda = 0.5; s.als_on = false; s.als_notch = true; s.als_adapt = true;
+  s.static_gain = 10.0; s.agc_on = true;
+  s.nb_thr = 1.2; s.nb_on = true;
+  s.aud_on = false; s.aud_id = 0;
+  do_init(h, c);
+}
+
+int apply_one(sdr_batch *h, uint32_t c, uint32_t op, float a0, float a1, float a2) {
+  Shadow &s = h->sh[c];
+  switch (op) {
+    case SDR_SET_setMute: s.muted = (a0 != 0.0f); break;
+    case SDR_SET_setInputGain: { float g = a0; if (g > 10.0) g = 10.0; if (g < 0.0) g = 0.0;
+      s.in_gain = g; s.in_gain_i = s.in_gain * s.gain_balance; s.in_gain_q = s.in_gain; } break;
+    case SDR_SET_setIQgainBalance: { float bal = sqrtf(a0); /* a LOCAL in the reference: the member stays 1 (Q7) */
+      s.in_gain_i = s.in_gain * bal; s.in_gain_q = s.in_gain / bal; } break;
+    case SDR_SET_setDemodMode: return set_mode(h, c, (int)a0);
+    case SDR_SET_enableAudioFilter: s.aud_on = true; break;
+    case SDR_SET_disableAudioFilter: s.aud_on = false; break;
+    case SDR_SET_setOutputGain: s.out_gain = a0; break;
+    case SDR_SET_setAudioFilter: { int id = (int)a0;
+      if (id < 0 || id > SDR_AUDIO_BYPASS) return fail(SDR_ERR_MODE, "setAudioFilter: id outside 0..10");
+      if (id == SDR_AUDIO_BYPASS) s.aud_on = false;
+      else { s.aud_set = id; h->pend_reset[c] |= SDRK_R_AUD; }
+      s.aud_id = id; } break;
+    case SDR_SET_enableALSfilter: s.als_on = true; h->pend_reset[c] |= SDRK_R_ALS; break;
+    case SDR_SET_disableALSfilter: s.als_on = false; break;
+    case SDR_SET_setALSfilterNotch: s.als_notch = true; break;
+    case SDR_SET_setALSfilterPeak: s.als_notch = false; break;
+    case SDR_SET_setALSfilterAdaptive: s.als_adapt = true; break;
+    case SDR_SET_setALSfilterStatic: s.als_adapt = false; break;
+    case SDR_SET_setALSfilterParams: {
+      int m = (int16_t)(unsigned)a0; if (m >= SDR_BLOCK_SAMPLES) m = SDR_BLOCK_SAMPLES;
+      int d = (int16_t)a2;
+      /* the reference indexes _als_in[(i - delay) - j] with i >= 128: anything reaching below 0 is out of bounds there */
+      if (m < 0 || d < 0 || m + d > 129) return fail(SDR_ERR_UNSUPPORTED, "setALSfilterParams: M + delay > 129 or negative");
+      s.als_m = m; s.als_lambda = a1; s.als_delay = d; } break;
+    case SDR_SET_enableAGC: s.agc_on = true; break;
+    case SDR_SET_disableAGC: s.agc_on = false; break;
+    case SDR_SET_setAGCthreshold: s.thr = a0; s.lut_id = lut_for(h, s.thr, s.slope, s.knee); break;
+    case SDR_SET_setAGCslope: s.slope = a0; s.lut_id = lut_for(h, s.thr, s.slope, s.knee); break;
+    case SDR_SET_setAGCmode: { int m = (int16_t)a0;
+      if (m < 0 || m > 3) return fail(SDR_ERR_MODE, "setAGCmode: mode outside 0..3");
+      if (m == SDR_AGC_OFF) s.agc_on = false;
+      else if (m == SDR_AGC_FAST) { agc_attack(s, 2.0); agc_release(s, 100.0); agc_hang(s, 100.0); s.agc_on = true; }
+      else if (m == SDR_AGC_MEDIUM) { agc_attack(s, 5.0); agc_release(s, 250.0); agc_hang(s, 500.0); s.agc_on = true; }
+      else { agc_attack(s, 10.0); agc_release(s, 500.0); agc_hang(s, 2000.0); s.agc_on = true; } } break;
+    case SDR_SET_setAGCkneeWidth: s.knee = a0; s.lut_id = lut_for(h, s.thr, s.slope, s.knee); break;
+    case SDR_SET_setAGCattackTime: agc_attack(s, a0); break;
+    case SDR_SET_setAGCreleaseTime: agc_release(s, a0); break;
+    case SDR_SET_setAGChangTime: agc_hang(s, a0); break;
+    case SDR_SET_setAGCstaticGain: s.static_gain = a0; break;
+    case SDR_SET_enableNoiseBlanker: s.nb_on = true; h->pend_reset[c] |= SDRK_R_NB; break;
+    case SDR_SET_disableNoiseBlanker: s.nb_on = false; break;
+    case SDR_SET_setNoiseBlankerThreshold: s.nb_thr = a0; h->pend_reset[c] |= SDRK_R_NB; break;
+    case SDR_SET_setNoiseBlankerThresholdDb: s.nb_thr = powf(10.0, (a0 / 20.0)); h->pend_reset[c] |= SDRK_R_NB; break;
+    case SDR_SET_init: do_init(h, c); break;
+    default: return fail(SDR_ERR_ARG, "unknown setter id");
+  }
+  h->cfg_dirty = true;
+  return 0;
+}
+
+void resolve(const Shadow &s, SdrChanCfg &c) {
+  memset(&c, 0, sizeof c);
+  c.mode = s.mode;
+  c.flags = (s.nb_on ? CF_NB : 0) | (s.aud_on ? CF_AUD : 0) | (s.agc_on ? CF_AGC : 0) | (s.als_on ? CF_ALS : 0) |
+            (s.als_notch ? CF_ALS_NOTCH : 0) | (s.als_adapt ? CF_ALS_ADAPT : 0) | (s.muted ? CF_MUTED : 0);
+  c.in_gain_i = s.in_gain_i; c.in_gain_q = s.in_gain_q; c.out_gain = s.out_gain;
+  const float two_pi = (float)(2.0 * PI_D);
+  c.ssb_phase_inc = (-s.freq_shift) * (two_pi / FS); /* freq_shifter's phase_inc, H:510, with freq_shift = -_freq_shift (C:86) */
+  c.if_set = s.if_set; c.aud_set = s.aud_set;
+  c.agc_a_att = s.a_att; c.agc_b_att = s.b_att; c.agc_a_rel = s.a_rel; c.agc_b_rel = s.b_rel; c.agc_static_gain = s.static_gain;
+  c.agc_hang_count = s.hang_count; c.agc_lut = s.lut_id;
+  c.nb_thr = s.nb_thr; c.als_m = s.als_m; c.als_delay = s.als_delay; c.als_lambda = s.als_lambda;
+}
+
+void build_groups(sdr_batch *h) {
+  h->h_groups.clear();
+  for (int cls = 0; cls < 2; cls++) {
+    SdrGroup g; int fill = 0;
+    auto flush = [&]() {
+      if (!fill) return;
+      for (int l = fill; l < SDR_LANES; l++) g.cid[l] = -1;
+      h->h_groups.push_back(g); fill = 0;
+    };
+    for (uint32_t c = 0; c < h->n_ch; c++) {
+      const Shadow &s = h->sh[c];
+      int k = (s.mode == SDR_AM || s.mode == SDR_SAM) ? CLS_ENV : CLS_SSB;
+      if (k != cls) continue;
+      if (!fill) { memset(&g, 0, sizeof g); g.cls = cls; }
+      g.cid[fill++] = (int32_t)c;
+      if (fill == SDR_LANES) flush();
+    }
+    flush();
+  }
+  h->n_groups = (uint32_t)h->h_groups.size();
+}
+
+int sync_config(sdr_batch *h, void *stream) {
+  if (h->luts_dirty) {
+    size_t need = h->luts.size() * sizeof(float);
+    if (need > h->luts_cap) {
+      if (h->d_luts) { if (dev_sync(h->last_stream)) return SDR_ERR_CUDA; dev_free(h->d_luts); }
+      size_t cap = std::max(need * 2, (size_t)SDR_AGC_LUT_STRIDE * 4 * 16);
+      if (dev_alloc((void **)&h->d_luts, cap)) return SDR_ERR_NOMEM;
+      h->luts_cap = cap;
+    }
+    if (h2d(h->d_luts, h->luts.data(), need, stream)) return SDR_ERR_CUDA;
+    h->luts_dirty = false;
+  }
+  if (h->cfg_dirty) {
+    for (uint32_t c = 0; c < h->n_ch; c++) resolve(h->sh[c], h->h_cfg[c]);
+    if (h2d(h->d_cfg, h->h_cfg.data(), sizeof(SdrChanCfg) * h->n_ch, stream)) return SDR_ERR_CUDA;
+    h->cfg_dirty = false;
+    h->groups_dirty = true; /* group feature summaries depend on the flags */
+  }
+  if (h->groups_dirty) {
+    build_groups(h);
+    for (SdrGroup &g : h->h_groups) { g.feat = 0; for (int l = 0; l < SDR_LANES; l++) if (g.cid[l] >= 0) g.feat |= h->h_cfg[g.cid[l]].flags; }
+    size_t need = sizeof(SdrGroup) * std::max<size_t>(h->h_groups.size(), 1);
+    if (need > h->groups_cap) {
+      if (h->d_groups) { if (dev_sync(h->last_stream)) return SDR_ERR_CUDA; dev_free(h->d_groups); }
+      if (dev_alloc((void **)&h->d_groups, need)) return SDR_ERR_NOMEM;
+      h->groups_cap = need;
+    }
+    if (!h->h_groups.empty() && h2d(h->d_groups, h->h_groups.data(), sizeof(SdrGroup) * h->h_groups.size(), stream)) return SDR_ERR_CUDA;
+    h->groups_dirty = false;
+  }
+  /* replay pending state re-initialisations */
+  std::vector<uint32_t> ch, mk;
+  for (uint32_t c : h->dirty_list) if (h->pend_reset[c]) { ch.push_back(c); mk.push_back(h->pend_reset[c]); h->pend_reset[c] = 0; }
+  h->dirty_list.clear();
+  if (!ch.empty()) {
+    if (ch.size() > h->reset_cap) {
+      if (h->d_reset_ch) { if (dev_sync(h->last_stream)) return SDR_ERR_CUDA; dev_free(h->d_reset_ch); dev_free(h->d_reset_mask); }
+      size_t cap = std::max<size_t>(ch.size() * 2, 1024);
+      if (dev_alloc((void **)&h->d_reset_ch, cap * 4) || dev_alloc((void **)&h->d_reset_mask, cap * 4)) return SDR_ERR_NOMEM;
+      h->reset_cap = cap;
+    }
+    for (size_t o = 0; o < ch.size(); o += 65535) { /* gridDim.y limit */
+      uint32_t n = (uint32_t)std::min<size_t>(65535, ch.size() - o);
+      if (h2d(h->d_reset_ch + o, ch.data() + o, n * 4, stream) || h2d(h->d_reset_mask + o, mk.data() + o, n * 4, stream)) return SDR_ERR_CUDA;
+      /* the staging vectors die at scope exit: the copies above are from pageable memory and complete before return */
+      int e = sdrk_launch_reset(h->d_state, h->ch_stride, h->d_reset_ch + o, h->d_reset_mask + o, n, stream);
+      if (e) return fail(SDR_ERR_CUDA, "reset kernel launch failed");
+      h->launches++;
+    }
+  }
+  return 0;
+}
+
+int check_plane(const void *p, size_t pitch, int fmt, uint32_t n_blocks, const char *what) {
+  if (!p) return fail(SDR_ERR_ARG, std::string(what) + ": null plane");
+  if (fmt != SDR_FMT_I16 && fmt != SDR_FMT_F32) return fail(SDR_ERR_ARG, std::string(what) + ": unknown format");
+  size_t es = fmt == SDR_FMT_F32 ? 4 : 2;
+  if (pitch < (size_t)n_blocks * SDR_BLOCK_SAMPLES) return fail(SDR_ERR_ARG, std::string(what) + ": pitch shorter than the call");
+  if ((pitch * es) % 16 != 0 || ((uintptr_t)p) % 16 != 0) return fail(SDR_ERR_ARG, std::string(what) + ": rows must be 16-byte aligned");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sdr_batch_last_error(void) { return g_err.c_str(); }
+const char *sdr_batch_version(void) {
+#ifdef SDR_EMU
+  return "sdr_batch 0.1 (HOST EMULATION BUILD - tests only)";
+#else
+  return "sdr_batch 0.1 (sm_100a)";
+#endif
+}
+uint64_t sdr_batch_launch_count(const sdr_batch_t *h) { return h ? h->launches : 0; }
+
+void sdr_batch_destroy(sdr_batch_t *h) {
+  if (!h) return;
+  dev_select(h->desc.device);
+  dev_sync(h->last_stream);
+  dev_free(h->d_state); dev_free(h->d_cfg); dev_free(h->d_groups); dev_free(h->d_luts); dev_free(h->d_tabs);
+  dev_free(h->d_reset_ch); dev_free(h->d_reset_mask); dev_free(h->d_gather); dev_free(h->d_gather_ids); dev_free(h->d_gather_words);
+  dev_free(h->d_in_i); dev_free(h->d_in_q); dev_free(h->d_out);
+  delete h;
+}
+
+int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
+  if (!out || !desc || desc->n_channels == 0) return fail(SDR_ERR_ARG, "create: bad arguments");
+  *out = nullptr;
+  if (dev_select(desc->device)) return SDR_ERR_CUDA;
+  sdr_batch *h = new sdr_batch();
+  h->desc = *desc; h->n_ch = desc->n_channels;
+  h->ch_stride = ((size_t)h->n_ch + 31) / 32 * 32;
+  h->sh.resize(h->n_ch); h->pend_reset.assign(h->n_ch, 0); h->h_cfg.resize(h->n_ch);
+  h->cfg_dirty = h->groups_dirty = true; h->luts_dirty = false;
+  h->d_state = nullptr; h->d_cfg = nullptr; h->d_groups = nullptr; h->d_luts = nullptr; h->d_tabs = nullptr;
+  h->d_reset_ch = h->d_reset_mask = nullptr; h->reset_cap = h->luts_cap = h->groups_cap = 0;
+  h->d_gather = nullptr; h->d_gather_ids = h->d_gather_words = nullptr; h->gather_cap = 0;
+  h->d_in_i = h->d_in_q = h->d_out = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0;
+  h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
+
+  SdrTables *t = new SdrTables();
+  const uint32_t *ifs[4] = {SDR_TAB_IF_SSB, SDR_TAB_IF_CW, SDR_TAB_IF_WSPR, SDR_TAB_IF_AM};
+  const uint32_t *auds[10] = {SDR_TAB_AUDIO_AM, SDR_TAB_AUDIO_CW, SDR_TAB_AUDIO_WSPR, SDR_TAB_AUDIO_2100, SDR_TAB_AUDIO_2300,
+                              SDR_TAB_AUDIO_2500, SDR_TAB_AUDIO_2700, SDR_TAB_AUDIO_2900, SDR_TAB_AUDIO_3100, SDR_TAB_AUDIO_3300};
+  for (int s = 0; s < 4; s++) for (int i = 0; i < 20; i++) t->if_sets[s][i] = tabf(ifs[s], i);
+  for (int s = 0; s < 10; s++) for (int i = 0; i < 20; i++) t->aud_sets[s][i] = tabf(auds[s], i);
+  for (int i = 0; i < 20; i++) t->am_image[i] = tabf(SDR_TAB_AM_IMAGE, i);
+  for (int i = 0; i < 64; i++) t->hilbert[i] = tabf(SDR_TAB_HILBERT, i);
+  memset(t->sine, 0, sizeof t->sine);
+  for (int i = 0; i < 257; i++) t->sine[i] = tabf(SDR_TAB_SINE, i);
+
+  int rc = 0;
+  do {
+    if ((rc = sdrk_setup_device(t->hilbert)) != 0) { rc = fail(SDR_ERR_CUDA, "device setup failed (no sm_100a kernel image or no CUDA device)"); break; }
+    if ((rc = dev_alloc((void **)&h->d_state, sizeof(float) * SDR_STATE_WORDS * h->ch_stride)) != 0) break;
+    if ((rc = dev_zero(h->d_state, sizeof(float) * SDR_STATE_WORDS * h->ch_stride, nullptr)) != 0) break;
+    if ((rc = dev_alloc((void **)&h->d_cfg, sizeof(SdrChanCfg) * h->n_ch)) != 0) break;
+    if ((rc = dev_alloc((void **)&h->d_tabs, sizeof(SdrTables))) != 0) break;
+    if ((rc = h2d(h->d_tabs, t, sizeof(SdrTables), nullptr)) != 0) break;
+    /* power-on values that are not zero: _nb_AvgMag = 10.0 (H:242), _agc_is_active = true (H:230) */
+    if (sdrk_launch_fill_word(h->d_state, h->ch_stride, W_NB_AVG, 10.0f, h->n_ch, nullptr)) { rc = fail(SDR_ERR_CUDA, "fill kernel"); break; }
+    uint32_t one = 1; float onef; memcpy(&onef, &one, 4);
+    if (sdrk_launch_fill_word(h->d_state, h->ch_stride, W_AGC_ACTIVE, onef, h->n_ch, nullptr)) { rc = fail(SDR_ERR_CUDA, "fill kernel"); break; }
+    h->launches += 2;
+    if ((rc = dev_sync(nullptr)) != 0) break;
+  } while (0);
+  delete t;
+  if (rc) { std::string keep = g_err; sdr_batch_destroy(h); g_err = keep; return rc < 0 ? rc : SDR_ERR_CUDA; }
+  for (uint32_t c = 0; c < h->n_ch; c++) { construct(h, c); h->pend_reset[c] = 0; /* fresh state is already zero */ }
+  *out = h;
+  return SDR_OK;
+}
+
+int sdr_batch_set(sdr_batch_t *h, const uint32_t *ids, uint32_t n, uint32_t setter, float a0, float a1, float a2) {
+  if (!h) return fail(SDR_ERR_ARG, "null handle");
+  if (!ids) n = h->n_ch;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t c = ids ? ids[i] : i;
+    if (c >= h->n_ch) return fail(SDR_ERR_ARG, "channel id out of range");
+    int rc = apply_one(h, c, setter, a0, a1, a2);
+    if (rc) return rc;
+    if (h->pend_reset[c]) h->dirty_list.push_back(c);
+  }
+  return SDR_OK;
+}
+
+int sdr_batch_configure(sdr_batch_t *h, const sdr_setter_call *calls, uint32_t n_calls) {
+  if (!h || (!calls && n_calls)) return fail(SDR_ERR_ARG, "configure: bad arguments");
+  for (uint32_t i = 0; i < n_calls; i++) {
+    const sdr_setter_call &k = calls[i];
+    int rc;
+    if (k.channel == SDR_ALL_CHANNELS) rc = sdr_batch_set(h, nullptr, 0, k.setter, k.a0, k.a1, k.a2);
+    else rc = sdr_batch_set(h, &k.channel, 1, k.setter, k.a0, k.a1, k.a2);
+    if (rc) return rc;
+  }
+  return SDR_OK;
+}
+
+int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio,
+                             size_t out_pitch, int out_fmt, uint32_t n_blocks, void *stream) {
+  if (!h) return fail(SDR_ERR_ARG, "null handle");
+  if (n_blocks == 0) return fail(SDR_ERR_ARG, "n_blocks == 0");
+  if (h->desc.max_blocks_per_call && n_blocks > h->desc.max_blocks_per_call) return fail(SDR_ERR_ARG, "n_blocks > max_blocks_per_call");
+  if (n_blocks > (1u << 28)) return fail(SDR_ERR_ARG, "n_blocks too large");
+  int rc;
+  if ((rc = check_plane(I, in_pitch, in_fmt, n_blocks, "I")) || (rc = check_plane(Q, in_pitch, in_fmt, n_blocks, "Q")) ||
+      (rc = check_plane(audio, out_pitch, out_fmt, n_blocks, "audio")))
+    return rc;
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  if ((rc = sync_config(h, stream)) != 0) return rc;
+  SdrLaunch L;
+  memset(&L, 0, sizeof L);
+  L.in_i = I; L.in_q = Q; L.out = audio; L.in_pitch = in_pitch; L.out_pitch = out_pitch; L.in_fmt = in_fmt; L.out_fmt = out_fmt;
+  L.n_tiles = n_blocks * SDR_TPB; L.blk0_mod3 = (uint32_t)(h->blocks_done % 3);
+  L.cfg = h->d_cfg; L.state = h->d_state; L.ch_stride = h->ch_stride; L.groups = h->d_groups; L.agc_luts = h->d_luts; L.tabs = h->d_tabs;
+  L.n_groups = h->n_groups;
+  int e = sdrk_launch_pipeline(&L, stream);
+  if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
+  h->launches++;
+  h->blocks_done += n_blocks;
+  h->last_stream = stream;
+  return SDR_OK;
+}
+
+int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio,
+                           size_t out_pitch, int out_fmt, uint32_t n_blocks) {
+  if (!h || !I || !Q || !audio) return fail(SDR_ERR_ARG, "process_host: bad arguments");
+  if (n_blocks == 0) return fail(SDR_ERR_ARG, "n_blocks == 0");
+  size_t ns = (size_t)n_blocks * SDR_BLOCK_SAMPLES;
+  if (in_pitch < ns || out_pitch < ns) return fail(SDR_ERR_ARG, "pitch shorter than the call");
+  size_t ies = in_fmt == SDR_FMT_F32 ? 4 : 2, oes = out_fmt == SDR_FMT_F32 ? 4 : 2;
+  size_t in_bytes = ns * ies * h->n_ch, out_bytes = ns * oes * h->n_ch;
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  if (in_bytes > h->stage_in_bytes) {
+    dev_sync(h->last_stream);
+    dev_free(h->d_in_i); dev_free(h->d_in_q); h->d_in_i = h->d_in_q = nullptr; h->stage_in_bytes = 0;
+    if (dev_alloc(&h->d_in_i, in_bytes) || dev_alloc(&h->d_in_q, in_bytes)) return SDR_ERR_NOMEM;
+    h->stage_in_bytes = in_bytes;
+  }
+  if (out_bytes > h->stage_out_bytes) {
+    dev_sync(h->last_stream);
+    dev_free(h->d_out); h->d_out = nullptr; h->stage_out_bytes = 0;
+    if (dev_alloc(&h->d_out, out_bytes)) return SDR_ERR_NOMEM;
+    h->stage_out_bytes = out_bytes;
+  }
+  if (h2d_2d(h->d_in_i, ns * ies, I, in_pitch * ies, ns * ies, h->n_ch, nullptr)) return SDR_ERR_CUDA;
+  if (h2d_2d(h->d_in_q, ns * ies, Q, in_pitch * ies, ns * ies, h->n_ch, nullptr)) return SDR_ERR_CUDA;
+  int rc = sdr_batch_process_device(h, h->d_in_i, h->d_in_q, ns, in_fmt, h->d_out, ns, out_fmt, n_blocks, nullptr);
+  if (rc) return rc;
+  if (d2h_2d(audio, out_pitch * oes, h->d_out, ns * oes, ns * oes, h->n_ch, nullptr)) return SDR_ERR_CUDA;
+  if (dev_sync(nullptr)) return SDR_ERR_CUDA;
+  return SDR_OK;
+}
+
+static int gather_words(sdr_batch_t *h, const uint32_t *ids, uint32_t n, const uint32_t *words, uint32_t nw, std::vector<float> &out) {
+  size_t tot = (size_t)n * nw;
+  if (tot > h->gather_cap) {
+    dev_free(h->d_gather); dev_free(h->d_gather_ids); dev_free(h->d_gather_words);
+    h->d_gather = nullptr; h->d_gather_ids = h->d_gather_words = nullptr; h->gather_cap = 0;
+    if (dev_alloc((void **)&h->d_gather, tot * 4) || dev_alloc((void **)&h->d_gather_ids, (size_t)n * 4) ||
+        dev_alloc((void **)&h->d_gather_words, 64 * 4))
+      return SDR_ERR_NOMEM;
+    h->gather_cap = tot;
+  }
+  void *s = h->last_stream;
+  if (ids && h2d(h->d_gather_ids, ids, (size_t)n * 4, s)) return SDR_ERR_CUDA;
+  if (h2d(h->d_gather_words, words, (size_t)nw * 4, s)) return SDR_ERR_CUDA;
+  if (sdrk_launch_gather(h->d_state, h->ch_stride, ids ? h->d_gather_ids : nullptr, n, h->d_gather_words, nw, h->d_gather, s))
+    return fail(SDR_ERR_CUDA, "gather kernel launch failed");
+  h->launches++;
+  out.resize(tot);
+  if (d2h(out.data(), h->d_gather, tot * 4, s)) return SDR_ERR_CUDA;
+  if (dev_sync(s)) return SDR_ERR_CUDA;
+  return 0;
+}
+
+int sdr_batch_get_status(sdr_batch_t *h, const uint32_t *ids, uint32_t n, sdr_channel_status *out) {
+  if (!h || !out) return fail(SDR_ERR_ARG, "get_status: bad arguments");
+  if (n == 0) return SDR_OK;
+  for (uint32_t i = 0; i < n; i++) if ((ids ? ids[i] : i) >= h->n_ch) return fail(SDR_ERR_ARG, "channel id out of range");
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  const uint32_t words[8] = {W_AGC_GAIN, W_AGC_ACTIVE, W_AGC_CARRIER, W_SAM_FREQ, W_SAM_LOCKED, W_NB_AVG, W_NB_HIT, W_PH_SSB};
+  std::vector<float> v;
+  int rc = gather_words(h, ids, n, words, 8, v);
+  if (rc) return rc;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t c = ids ? ids[i] : i;
+    const Shadow &s = h->sh[c];
+    sdr_channel_status &o = out[i];
+    memset(&o, 0, sizeof o);
+    const float *w = &v[(size_t)i * 8];
+    uint32_t u;
+    o.tuning_offset = s.freq_shift; o.mode = s.mode; o.audio_filter = s.aud_id; o.muted = s.muted;
+    int m = s.mode; /* getBPFlower/upper, C:259-273 */
+    if (m == SDR_USB || m == SDR_LSB) { o.bpf_lower = IF_CENTER - BW_SSB / 2.0; o.bpf_upper = IF_CENTER + BW_SSB / 2.0; }
+    else if (m == SDR_CW_USB || m == SDR_CW_LSB) { o.bpf_lower = IF_CENTER - BW_CW / 2.0; o.bpf_upper = IF_CENTER + BW_CW / 2.0; }
+    else if (m == SDR_AM || m == SDR_SAM) { o.bpf_lower = IF_CENTER - BW_AM / 2.0; o.bpf_upper = IF_CENTER + BW_AM / 2.0; }
+    else if (m == SDR_WSPR) { o.bpf_lower = IF_CENTER - BW_WSPR / 2.0; o.bpf_upper = IF_CENTER + -BW_WSPR / 2.0; /* `+-` typo kept, Q11 */ }
+    o.agc_gain = w[0]; memcpy(&u, &w[1], 4); o.agc_active = u != 0; o.am_carrier = w[2]; o.sam_frequency = w[3];
+    memcpy(&u, &w[4], 4); o.sam_locked = u != 0; o.nb_average = w[5]; memcpy(&u, &w[6], 4); o.nb_detected = u != 0;
+    o.agc_enabled = s.agc_on; o.nb_enabled = s.nb_on; o.als_enabled = s.als_on; o.als_notch = s.als_notch; o.als_adaptive = s.als_adapt;
+    o.audio_filter_enabled = s.aud_on;
+  }
+  return SDR_OK;
+}
+
+int sdr_batch_get_agc_lookup(sdr_batch_t *h, uint32_t channel, float *out129) {
+  if (!h || !out129 || channel >= h->n_ch) return fail(SDR_ERR_ARG, "get_agc_lookup: bad arguments");
+  memcpy(out129, &h->luts[(size_t)h->sh[channel].lut_id * SDR_AGC_LUT_STRIDE], 129 * sizeof(float));
+  return SDR_OK;
+}
+
+int sdr_batch_peek_state(sdr_batch_t *h, uint32_t channel, uint32_t word, float *out) {
+  if (!h || !out || channel >= h->n_ch || word >= SDR_STATE_WORDS) return fail(SDR_ERR_ARG, "peek_state: bad arguments");
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  std::vector<float> v;
+  int rc = gather_words(h, &channel, 1, &word, 1, v);
+  if (rc) return rc;
+  *out = v[0];
+  return SDR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+/* sdr_kernel.cu -- sm_100a kernels of the batched receiver chain and their launchers.
+ *
+ * sdr_pipeline_kernel: one CTA per 32-channel group, 11 warps = 11 pipeline stages (see
+ * sdr_pipeline.cuh).  Build flags matter for parity: -fmad=false (no FMA contraction; the reference
+ * rounds every product and sum separately), IEEE division and square root (nvcc defaults), no FTZ.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sdr_kernel.h"
+#include "sdr_pipeline.cuh"
+
+using namespace sdrk;
+
+__constant__ float c_hilbert[64]; /* compact Hilbert half, H:757-774: constant-bank operands of the unrolled FIR */
+
+template <class Body>
+__device__ __forceinline__ void pipeline_loop(uint32_t n_tiles, int delay, int dmax, Body body) {
+  __syncthreads(); /* histories and tables are in shared memory */
+  const uint32_t steps = n_tiles + (uint32_t)dmax;
+  for (uint32_t s = 0; s < steps; s++) {
+    const long long tau = (long long)s - delay;
+    if (tau >= 0 && tau < (long long)n_tiles) body((uint32_t)tau);
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void run_ssb(const Ctx &x, int warp, int lane) {
+  const uint32_t n = x.L->n_tiles;
+  switch (warp) {
+    case 0: { RoleIn r; r.load(x, lane); pipeline_loop(n, D_IN, D_SSB_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case 1: case 2: {
+      const int rail = warp - 1;
+      RoleBiquad r; r.load(x, lane, 0, rail);
+      pipeline_loop(n, D_IF, D_SSB_MAX, [&](uint32_t t) { r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true); });
+      r.save(x, 0, rail);
+    } break;
+    case 3: { RoleNco r; r.load(x, lane); pipeline_loop(n, D_NCO, D_SSB_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
+    case 4: case 5: case 6: case 7: {
+      const int sub = warp - 4;
+      RoleHilbert r; r.load(x, lane, sub);
+      pipeline_loop(n, D_HIL, D_SSB_MAX, [&](uint32_t t) { r.step(x, c_hilbert, lane, sub, t); });
+      r.save(x, lane, sub);
+    } break;
+    case 8: {
+      RoleBiquad r; r.load(x, lane, 1, 0);
+      pipeline_loop(n, D_AUD, D_SSB_MAX, [&](uint32_t t) { r.step(x.tile(S_A, t & 1), x.tile(S_B, t & 1), lane, r.on); });
+      r.save(x, 1, 0);
+    } break;
+    case 9: {
+      RoleAgc r; r.load(x, lane);
+      pipeline_loop(n, D_AGC, D_SSB_MAX, [&](uint32_t t) { r.step(x.tile(S_B, t & 1), x.tile(S_C, t % NC), lane, 0.0f); });
+      r.save(x);
+    } break;
+    default: {
+      RoleOut r; r.load(x, lane, S_C, S_ALSC);
+      pipeline_loop(n, D_OUT, D_SSB_MAX, [&](uint32_t t) { r.step(x, lane, t, S_C, S_ALSC); });
+      r.save(x, lane, S_C, S_ALSC);
+    } break;
+  }
+}
+
+__device__ __forceinline__ void run_env(const Ctx &x, int warp, int lane) {
+  const uint32_t n = x.L->n_tiles;
+  switch (warp) {
+    case 0: { RoleIn r; r.load(x, lane); pipeline_loop(n, D_IN, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case 1: case 2: {
+      const int rail = warp - 1;
+      RoleBiquad r; r.load(x, lane, 0, rail);
+      pipeline_loop(n, D_IF, D_ENV_MAX, [&](uint32_t t) { r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true); });
+      r.save(x, 0, rail);
+    } break;
+    case 3: { RolePll r; r.load(x, lane); pipeline_loop(n, E_D_PLL, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
+    case 4: { RoleNco2 r; r.load(x, lane); pipeline_loop(n, E_D_NCO2, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
+    case 5: case 6: {
+      const int rail = warp - 5;
+      RoleBiquad r; r.load(x, lane, 2, rail);
+      pipeline_loop(n, E_D_IMG, D_ENV_MAX, [&](uint32_t t) {
+        r.step(x.tile(E_Z2, (t & 1) * 2 + rail), x.tile(E_V, (t & 1) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
+      });
+      r.save(x, 2, rail);
+    } break;
+    case 7: { RoleMag r; r.load(x, lane); pipeline_loop(n, E_D_MAG, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
+    case 8: {
+      RoleBiquad r; r.load(x, lane, 1, 0);
+      pipeline_loop(n, E_D_AUD, D_ENV_MAX, [&](uint32_t t) { r.step(x.tile(E_A, t & 1), x.tile(E_B, t % NB_RING), lane, r.on); });
+      r.save(x, 1, 0);
+    } break;
+    case 9: {
+      RoleAgc r; r.load(x, lane);
+      pipeline_loop(n, E_D_AGC, D_ENV_MAX, [&](uint32_t t) {
+        r.step(x.tile(E_B, t % NB_RING), x.tile(E_C, t % NC), lane, x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane]);
+      });
+      r.save(x);
+    } break;
+    default: {
+      RoleOut r; r.load(x, lane, E_C, E_ALSC);
+      pipeline_loop(n, E_D_OUT, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t, E_C, E_ALSC); });
+      r.save(x, lane, E_C, E_ALSC);
+    } break;
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel(const __grid_constant__ SdrLaunch L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx x;
+  x.L = &L;
+  x.G = &L.groups[blockIdx.x];
+  x.smem = smem;
+  for (int i = threadIdx.x; i < 257; i += SDR_THREADS) x.f(S_SINE)[i] = L.tabs->sine[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (x.G->cls == CLS_SSB) run_ssb(x, warp, lane);
+  else run_env(x, warp, lane);
+}
+
+/* Zero (or re-seed) state words of listed channels: the side effects of the reference setters that
+ * re-initialise filter state / rings.  One thread per (entry, word). */
+extern "C" __global__ void sdr_reset_kernel(float *state, unsigned long long ch_stride, const uint32_t *chan, const uint32_t *mask,
+                                            uint32_t n) {
+  const uint32_t e = blockIdx.y;
+  if (e >= n) return;
+  const uint32_t c = chan[e], m = mask[e];
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < SDR_STATE_WORDS; w += gridDim.x * blockDim.x) {
+    bool z = false;
+    if ((m & SDRK_R_IF) && w >= W_IF_I && w < W_IF_Q + 16) z = true;
+    if ((m & SDRK_R_IMG) && w >= W_IMG_I && w < W_IMG_Q + 16) z = true;
+    if ((m & SDRK_R_AUD) && w >= W_AUD && w < W_AUD + 16) z = true;
+    if ((m & SDRK_R_ALS) && w >= W_ALS_C && w < W_ALS_H + 128) z = true;
+    if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING + 768) z = true;
+    if (z) state[(size_t)w * ch_stride + c] = 0.0f;
+  }
+}
+
+/* state word `w` of every channel := v (used once at create for non-zero power-on values) */
+extern "C" __global__ void sdr_fill_word_kernel(float *state, unsigned long long ch_stride, uint32_t w, float v, uint32_t n_ch) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_ch) state[(size_t)w * ch_stride + c] = v;
+}
+
+/* gather `n_words` listed state words of `n` listed channels into out[n][n_words] */
+extern "C" __global__ void sdr_gather_kernel(const float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n,
+                                             const uint32_t *words, uint32_t n_words, float *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * n_words) return;
+  uint32_t e = i / n_words, k = i % n_words;
+  uint32_t c = chan ? chan[e] : e;
+  out[i] = state[(size_t)words[k] * ch_stride + c];
+}
+
+extern "C" int sdrk_setup_device(const float *hilbert64) {
+  cudaError_t e = cudaMemcpyToSymbol(c_hilbert, hilbert64, 64 * sizeof(float));
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(sdr_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDR_SMEM_BYTES);
+  return (int)e;
+}
+
+extern "C" int sdrk_launch_pipeline(const SdrLaunch *L, void *stream) {
+  if (L->n_groups == 0) return 0;
+  sdr_pipeline_kernel<<<L->n_groups, SDR_THREADS, SDR_SMEM_BYTES, (cudaStream_t)stream>>>(*L);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sdrk_launch_reset(float *state, unsigned long long ch_stride, const uint32_t *chan, const uint32_t *mask, uint32_t n,
+                                 void *stream) {
+  if (n == 0) return 0;
+  dim3 grid(4, n);
+  sdr_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(state, ch_stride, chan, mask, n);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sdrk_launch_fill_word(float *state, unsigned long long ch_stride, uint32_t w, float v, uint32_t n_ch, void *stream) {
+  sdr_fill_word_kernel<<<(n_ch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state, ch_stride, w, v, n_ch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sdrk_launch_gather(const float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n,
+                                  const uint32_t *words, uint32_t n_words, float *out, void *stream) {
+  uint32_t tot = n * n_words;
+  if (tot == 0) return 0;
+  sdr_gather_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state, ch_stride, chan, n, words, n_words, out);
+  return (int)cudaGetLastError();
+}
