@@ -180,3 +180,55 @@ extern "C" int sdrk_launch_gather(const float *state, unsigned long long ch_stri
   sdr_gather_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state, ch_stride, chan, n, words, n_words, out);
   return (int)cudaGetLastError();
 }
+
+/* ---- FP32 pipe microbenchmark: the denominator of the FP32 roofline (MEASURED_PEAKS.json has no FP32 entry).
+ * kind 0: dependent FFMA chains (2 flop / instruction, what a contracting build could reach);
+ * kind 1: alternating FMUL / FADD chains (1 flop / instruction: the instruction mix this parity-exact build issues).
+ * 8 independent chains per thread hide the 4-cycle pipe latency. */
+template <int KIND>
+__global__ void __launch_bounds__(256) sdr_fp32_peak_kernel(float *out, int iters, float a, float b) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = a + (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (KIND == 0) v[i] = __fmaf_rn(v[i], a, b);
+        else { v[i] = __fmul_rn(v[i], a); v[i] = __fadd_rn(v[i], b); }
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += v[i];
+  if (s == 123.456f) out[0] = s; /* keep the chains alive */
+}
+
+/* returns instructions/s (FP32-pipe lane-instructions per second) in *lane_ips and elapsed ms; 0 on success */
+extern "C" int sdrk_fp32_peak(int kind, int iters, double *lane_ips, float *ms_out) {
+  float *d = nullptr;
+  if (cudaMalloc(&d, 4) != cudaSuccess) return 1;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * 8, block = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int rep = 0; rep < 2; rep++) { /* first pass warms up */
+    cudaEventRecord(e0);
+    if (kind == 0) sdr_fp32_peak_kernel<0><<<grid, block>>>(d, iters, 0.999f, 0.001f);
+    else sdr_fp32_peak_kernel<1><<<grid, block>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return 2; }
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double instr = (double)grid * block * (double)iters * 64.0 * (kind == 0 ? 1.0 : 2.0);
+  *lane_ips = instr / (ms * 1e-3);
+  *ms_out = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return 0;
+}

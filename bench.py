@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the batched receiver chain (contract: one JSON line on rank 0).
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on, one GPU's worth per rank):
+4 096 independent channels in mixed CW_LSB/CW_USB/LSB/USB modes, noise blanker (10 dB) + AGC (medium) + audio
+band-pass on, synthetic two-tone / keyed-carrier IF signals with impulse noise.  A "step" is one
+sdr_batch_process call advancing every channel by --blocks-per-step 128-sample blocks (state carries from step
+to step).  `value` is whole-job channel-samples/s with the float32 I/Q planes already resident in HBM;
+`e2e` is the same through sdr_batch_process_host with pinned HOST int16 planes (the reference's audio_block_t
+wire format), copies inside the timed region.
+
+  python bench.py [--gpus N --steps K --warmup W]          our CUDA path
+  python bench.py --impl reference ...                      the reference's own CPU update() on all host cores
+Under torchrun every rank drives its own GPU and its own 4 096 channels (weak scaling); there is no data-path
+collective, NCCL only reduces the counters.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "channel_samples_per_s"
+UNIT = "Msps"
+CHANNELS_PER_GPU = 4096
+CONFIG_ID = 2
+FLOP_PER_SAMPLE = 364.0     # SSB/CW core 345 + noise blanker 19 (algorithmic flop per channel-sample)
+INSTR_PER_SAMPLE = 364.0    # the same operations issued unfused (parity forbids FMA contraction)
+BYTES_PER_SAMPLE = 12.0     # 8 B in (f32 I + f32 Q) + 4 B out per channel-sample
+HBM_FALLBACK_GBS = 6650.0
+
+
+def shard_range(total, rank, world):
+    """Contiguous channel range of `rank`."""
+    return total * rank // world, total * (rank + 1) // world
+
+
+def gather_counters(samples, ms, world, device):
+    """Sum of samples and max of elapsed ms over ranks: the only inter-rank traffic of the whole job."""
+    import torch
+    import torch.distributed as dist
+    if world > 1 and dist.is_initialized():
+        t = torch.tensor([samples], dtype=torch.float64, device=device if device is not None else "cpu")
+        m = torch.tensor([ms], dtype=torch.float64, device=device if device is not None else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        return dict(samples=float(t.item()), max_ms=float(m.item()))
+    return dict(samples=float(samples), max_ms=float(ms))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _pump(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_planes(dev, first_channel, n_channels, n_samples, seed):
+    """Config-2 style IF signals, generated on the device (int16 I/Q + the per-channel setter lists)."""
+    import torch
+    import signals as S
+    f = np.zeros((n_channels, 2)); amp = np.zeros((n_channels, 2)); keyed = np.zeros(n_channels, bool); off = np.zeros(n_channels, np.int64)
+    calls = []
+    for r in range(n_channels):
+        c = first_channel + r
+        m = S.channel_mode(CONFIG_ID, c)
+        if m in (S.LSB, S.USB):
+            f1 = 300.0 + 900.0 * S._unit(S.chash(CONFIG_ID, c, 2)); f2 = 1300.0 + 1200.0 * S._unit(S.chash(CONFIG_ID, c, 3))
+            f[r] = [S._audio_to_if(m, f1), S._audio_to_if(m, f2)]; amp[r] = [0.2, 0.2]
+        else:
+            f[r] = [S._audio_to_if(m, 700.0), 0.0]; amp[r] = [0.3, 0.0]; keyed[r] = True
+        off[r] = S.chash(CONFIG_ID, c, 5) % 11025
+        calls += [(r,) + tuple(e[2:]) for e in S.channel_events(CONFIG_ID, c, 0)]
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    I = torch.empty((n_channels, n_samples), dtype=torch.int16, device=dev)
+    Q = torch.empty_like(I)
+    t = torch.arange(n_samples, device=dev, dtype=torch.float64)
+    for a in range(0, n_channels, 256):
+        z = slice(a, min(a + 256, n_channels))
+        fz = torch.tensor(f[z], device=dev); az = torch.tensor(amp[z], device=dev)
+        ph0 = 2.0 * np.pi / 44100.0 * fz[:, 0:1] * t[None, :]
+        ph1 = 2.0 * np.pi / 44100.0 * fz[:, 1:2] * t[None, :]
+        key = torch.where(torch.tensor(keyed[z], device=dev)[:, None], ((t[None, :] // (44100.0 / 40.0)).long() & 1) == 0, True)
+        re = az[:, 0:1] * torch.cos(ph0) * key + az[:, 1:2] * torch.cos(ph1)
+        im = az[:, 0:1] * torch.sin(ph0) * key + az[:, 1:2] * torch.sin(ph1)
+        re = re + 0.01 * torch.randn(re.shape, generator=g, device=dev, dtype=torch.float64)
+        im = im + 0.01 * torch.randn(im.shape, generator=g, device=dev, dtype=torch.float64)
+        burst = ((t[None, :].long() - torch.tensor(off[z], device=dev)[:, None]) % 11025) < 3
+        re = torch.where(burst, 0.9, re); im = torch.where(burst, 0.9, im)
+        I[z] = torch.round(re.clamp(-1, 1) * 32767.0).to(torch.int16)
+        Q[z] = torch.round(im.clamp(-1, 1) * 32767.0).to(torch.int16)
+    return I, Q, calls
+
+
+def cpu_reference_rate(seconds, cores):
+    """The reference's own CPU update() (oracle/_ref, unmodified source) or, if absent, the oracle port, on `cores` workers."""
+    import signals as S
+    from oracle import ref_client as rc
+    chans = S.sample_channels(CONFIG_ID, CHANNELS_PER_GPU, max(cores, 8))[:max(cores, 1)]
+    I, Q, ev = S.make(CONFIG_ID, chans, 64)
+    sample = "%d sampled config-2 channels x 64 blocks streamed round-robin for %.0f s, one channel per worker" % (len(chans), seconds)
+    if rc.available():
+        r = rc.bench(I, Q, ev, seconds, cores)
+        return dict(value=r["sps_update_only"] / 1e6, unit=UNIT, cores=cores, kind="reference", sample=sample,
+                    wall_msps=r["sps_wall"] / 1e6)
+    from oracle import oracle_lib
+    oracle_lib.build()
+    reps, total, t0 = 0, 0.0, time.perf_counter()
+    Ir, Qr = np.tile(I, (1, 4)), np.tile(Q, (1, 4))
+    Ir = np.repeat(Ir, max(1, cores // len(chans) + 1), 0)[:cores]; Qr = np.repeat(Qr, max(1, cores // len(chans) + 1), 0)[:cores]
+    evr = []
+    for w in range(cores):
+        evr += [(w,) + tuple(e[1:]) for e in ev if e[0] == w % len(chans)]
+    busy = 0.0
+    while time.perf_counter() - t0 < seconds:
+        busy += oracle_lib.run(Ir, Qr, evr, threads=cores, want_pcm=False)["seconds"]
+        total += Ir.size; reps += 1
+    return dict(value=total / busy / 1e6, unit=UNIT, cores=cores, kind="port", sample=sample)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = 2.0
+    vals, t_steps = [], []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = cpu_reference_rate(per_step, cores)
+        if s >= args.warmup:
+            vals.append(r["value"]); t_steps.append((time.perf_counter() - t0) * 1e3)
+    v = float(np.mean(vals))
+    r["value"] = v
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=float(np.mean(t_steps)), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="BASELINE configs[1]: mixed CW/LSB/USB channels, NB+AGC+audio BPF; reference update() on host CPU",
+                            channels=r["cores"], step="%.0f s of streaming per step" % per_step),
+                cpu_baseline=r, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blocks-per-step", type=int, default=256)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import audiosdr_b200 as A
+    from audiosdr_b200 import api
+    A.build_library()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = api.load_library()
+    nch, nblk = CHANNELS_PER_GPU, args.blocks_per_step
+    ns = nblk * 128
+    first = rank * nch
+    I16, Q16, calls = synth_planes(dev, first, nch, ns, 0x5D120002 + rank)
+    If = (I16.to(torch.float32) / 32767.0).contiguous(); Qf = (Q16.to(torch.float32) / 32767.0).contiguous()
+    out = torch.empty((nch, ns), dtype=torch.float32, device=dev)
+    b = A.SdrBatch(nch, device=local)
+    b.configure(calls)
+    stream = torch.cuda.current_stream()
+
+    # ---- warm-up, with an untimed parity probe of sampled channels against the oracle on step 0
+    import signals as S
+    from oracle import oracle_lib
+    picks = sorted(set(S.sample_channels(CONFIG_ID, nch, 12, n_shards=2)))
+    parity = None
+    for w in range(max(args.warmup, 3)):
+        b.process(If, Qf, out, n_blocks=nblk, stream=stream)
+        if w == 0:
+            torch.cuda.synchronize()
+            got = out[picks].cpu().numpy()
+            hi, hq = If[picks].cpu().numpy(), Qf[picks].cpu().numpy()
+            ev = []
+            for row, c in enumerate(picks):
+                ev += S.channel_events(CONFIG_ID, first + c, row)
+            want = oracle_lib.run(hi, hq, ev, threads=os.cpu_count() or 1, want_pcm=False)["audio"]
+            parity = dict(channels=len(picks), samples=int(want.size), bit_exact=bool(np.array_equal(got.view(np.uint32), want.view(np.uint32))),
+                          max_abs_err=float(np.max(np.abs(got.astype(np.float64) - want))))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K launches, each timed with its own CUDA event pair on the launching stream
+    clk = ClockSampler(local); clk.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    l0 = b.launch_count
+    barrier()
+    ev0[0].record(stream)
+    for k in range(args.steps):
+        b.process(If, Qf, out, n_blocks=nblk, stream=stream)
+        ev0[k + 1].record(stream)
+    barrier()
+    launches = b.launch_count - l0
+    clocks = clk.stop()
+    total_ms = ev0[0].elapsed_time(ev0[-1])
+    per_launch_ms = [ev0[k].elapsed_time(ev0[k + 1]) for k in range(args.steps)]
+    cnt = gather_counters(float(nch) * ns * args.steps, total_ms, world, dev)
+    value = cnt["samples"] / (cnt["max_ms"] * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with HOST buffers (pinned int16 in, int16 out), copies inside the timed region
+    hI = torch.empty((nch, ns), dtype=torch.int16).pin_memory(); hQ = torch.empty_like(hI).pin_memory()
+    hO = torch.empty((nch, ns), dtype=torch.int16).pin_memory()
+    hI.copy_(I16); hQ.copy_(Q16)
+    nI, nQ, nO = hI.numpy(), hQ.numpy(), hO.numpy()
+    b.process_host(nI, nQ, nO, n_blocks=nblk)  # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.e2e_steps):
+        b.process_host(nI, nQ, nO, n_blocks=nblk)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    ecnt = gather_counters(float(nch) * ns * args.e2e_steps, e2e_ms, world, dev)
+    e2e = dict(value=ecnt["samples"] / (ecnt["max_ms"] * 1e-3) / 1e6, unit=UNIT, h2d_bytes_per_step=int(2 * nch * ns * 2),
+               d2h_bytes_per_step=int(nch * ns * 2), steps=args.e2e_steps, wire_format="int16 in / int16 out, pinned host memory",
+               api="sdr_batch_process_host")
+
+    # ---- rooflines of the dominant kernel (sdr_pipeline_kernel: one launch per step)
+    peaks, peak_src = measured_peaks()
+    launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    samples_per_launch = float(nch) * ns
+    hbm_gbs = BYTES_PER_SAMPLE * samples_per_launch / launch_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch_default_bench")
+        except Exception:
+            traffic = None
+    roofline = dict(bound="hbm", achieved=hbm_gbs, peak=float(peaks["hbm_gbs"]), unit="GB/s", frac=hbm_gbs / float(peaks["hbm_gbs"]),
+                    traffic=traffic, peak_source=peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
+                    kernel="sdr_pipeline_kernel", algorithmic_bytes_per_sample=BYTES_PER_SAMPLE,
+                    note="BASELINE.json quotes % of HBM roofline; the binding roofline of this chain is the FP32 pipe, see roofline_fp32")
+    fp32 = None
+    try:
+        import ctypes as C
+        ips = C.c_double(); ms = C.c_float()
+        lib.sdrk_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+        res = {}
+        for kind, name in ((0, "ffma"), (1, "fmul_fadd")):
+            if lib.sdrk_fp32_peak(kind, 4096, C.byref(ips), C.byref(ms)) == 0:
+                res[name] = ips.value
+        ach_flops = FLOP_PER_SAMPLE * samples_per_launch / launch_s
+        fp32 = dict(bound="fp32", achieved=ach_flops / 1e12, peak=2.0 * res["ffma"] / 1e12, unit="TFLOP/s",
+                    frac=ach_flops / (2.0 * res["ffma"]), peak_source="measured live: dependent-FFMA microbenchmark, 2 flop/instr",
+                    issue_frac=INSTR_PER_SAMPLE * samples_per_launch / launch_s / res["fmul_fadd"],
+                    issue_peak_ginstr_s=res["fmul_fadd"] / 1e9,
+                    note="issue_frac = algorithmic unfused FP32 instructions / measured FMUL+FADD issue rate (parity forbids FMA contraction)",
+                    algorithmic_flop_per_sample=FLOP_PER_SAMPLE)
+    except Exception as e:  # the microbenchmark is evidence, not the product
+        fp32 = dict(error=str(e))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_rate(args.cpu_seconds, os.cpu_count() or 1)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=cnt["max_ms"] / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload="BASELINE configs[1]: 4096 channels/GPU, mixed CW_LSB/CW_USB/LSB/USB, NB(10 dB)+AGC(medium)+audio BPF",
+                                channels_per_gpu=nch, blocks_per_step=nblk, samples_per_step=int(samples_per_launch),
+                                planes="float32 channel-major in HBM", l2="inputs per step %.0f MB >> 126 MB L2, no flush needed" % (2 * nch * ns * 4 / 1e6),
+                                parallelism="channels sharded, no collective"),
+                    e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_fp32=fp32, cpu_baseline=cpu,
+                    parity=parity, per_launch_ms=dict(mean=float(np.mean(per_launch_ms)), min=float(np.min(per_launch_ms)), max=float(np.max(per_launch_ms))))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,82 @@
+"""CPU tier: pipeline LOGIC of the product sources, run through the host emulation scaffold (tests/emu).
+
+The kernel's role bodies (audiosdr_b200/csrc/sdr_pipeline.cuh) and the whole host layer (sdr_host.cpp) are
+compiled for the host and stepped warp by warp with the kernel's barrier structure; results must equal the
+oracle bit for bit.  This proves delays, ring slots, state carry across calls, setter replay and grouping;
+the GPU tier (test_gpu_parity.py) proves the CUDA build itself.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import harness
+import signals as S
+from test_oracle import GOLDEN, load_golden
+
+
+@pytest.mark.parametrize("reverse", ["0", "1"])
+@pytest.mark.parametrize("cfg,nch,nblk", [(1, 1, 40), (2, 40, 30), (3, 6, 30), (4, 70, 24), (5, 5, 30)])
+def test_emulated_pipeline_matches_oracle(oracle, emu_lib, monkeypatch, cfg, nch, nblk, reverse):
+    monkeypatch.setenv("SDR_EMU_REVERSE", reverse)  # warp order inside a step must not matter
+    I, Q, ev = S.make(cfg, list(range(nch)), nblk)
+    o = oracle.run(I, Q, ev, threads=4)
+    a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(7, 1, 13), return_batch=True)
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+    p = harness.run_batch(emu_lib, I, Q, ev, chunks=(3, 11), out_dtype=np.int16)
+    assert np.array_equal(p, o["pcm"])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_emulated_pipeline_matches_reference_golden(emu_lib, path):
+    I, Q, ev, audio, pcm, status = load_golden(path)
+    a = harness.run_batch(emu_lib, I, Q, ev, chunks=(5, 2, 9))
+    assert harness.bits_equal(a, audio), harness.describe_mismatch(a, audio)
+
+
+def test_emulated_float32_planes(oracle, emu_lib):
+    I, Q, ev = S.make(2, list(range(33)), 20)
+    ev += [(c, 0, "setInputGain", 0.7) for c in range(0, 33, 3)] + [(c, 0, "setIQgainBalance", 1.05) for c in range(1, 33, 3)]
+    If = (I.astype(np.float32) / np.float32(32767.0)).astype(np.float32)
+    Qf = (Q.astype(np.float32) / np.float32(32767.0)).astype(np.float32)
+    o = oracle.run(If, Qf, ev, threads=4)
+    a = harness.run_batch(emu_lib, If, Qf, ev, chunks=(4, 9))
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+
+
+def test_emulated_setter_fuzz(oracle, emu_lib):
+    rng = np.random.default_rng(1234)
+    I, Q, ev = S.make(4, list(range(48)), 40)
+    ev += harness.fuzz_events(rng, 48, 40, 500)
+    o = oracle.run(I, Q, ev, threads=4)
+    a = harness.run_batch(emu_lib, I, Q, ev, chunks=(5, 2, 9))
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+
+
+def test_argument_errors(emu_lib):
+    import audiosdr_b200 as A
+    b = A.SdrBatch(3, _lib=emu_lib)
+    with pytest.raises(A.SdrError):
+        b.setDemodMode(0, 9)
+    with pytest.raises(A.SdrError):
+        b.setAudioFilter(0, 42)
+    with pytest.raises(A.SdrError):
+        b.set([7], "setMute", 1)
+    with pytest.raises(A.SdrError):
+        b.setALSfilterParams(0, 128, 0.5, 3)  # reaches before the reference's ring
+    I = np.zeros((3, 100), np.int16)  # not a whole block
+    with pytest.raises(A.SdrError):
+        b.process_host(I, I, n_blocks=0)
+
+
+def test_channel_results_do_not_depend_on_batch_position(oracle, emu_lib):
+    """Shard invariance: a channel gives the same bits whatever lane / group / batch hosts it."""
+    I, Q, ev = S.make(4, list(range(50)), 12)
+    full = harness.run_batch(emu_lib, I, Q, ev, chunks=(12,))
+    perm = np.random.default_rng(3).permutation(50)[:17]
+    sub_ev = []
+    for new, old in enumerate(perm):
+        sub_ev += [(new,) + tuple(e[1:]) for e in ev if e[0] == old]
+    sub = harness.run_batch(emu_lib, I[perm], Q[perm], sub_ev, chunks=(5, 7))
+    assert harness.bits_equal(sub, full[perm])

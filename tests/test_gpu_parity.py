@@ -1,0 +1,168 @@
+"""GPU tier: the CUDA library (sm_100a kernels) through the C ABI against the oracle and the reference goldens.
+
+Bar: BIT-EXACT float32 audio and int16 pcm on every mode (the build disables FMA contraction and follows the
+reference's operation order), which is far inside north_star's tolerance (1e-4 of full scale for the full
+chain, 1e-6 relative for the feed-forward mixer/FIR).  NaN samples (only the setter-fuzz cases produce them)
+compare equal as NaN: x86 and the GPU pick different NaN payloads.
+Nothing here reads /root/reference; the oracle is oracle/libsdr_oracle.so and tests/golden/*.npz.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import harness
+import signals as S
+from test_oracle import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL_FULL_CHAIN = 1e-4  # north_star: max abs error of full scale; we require 0
+
+
+def assert_same(a, want):
+    if a.dtype == np.float32:
+        nan_a, nan_w = np.isnan(a), np.isnan(want)
+        assert np.array_equal(nan_a, nan_w), "NaN pattern differs"
+        a = np.where(nan_a, np.float32(0), a); want = np.where(nan_w, np.float32(0), want)
+        err = float(np.max(np.abs(a.astype(np.float64) - want.astype(np.float64)))) if a.size else 0.0
+        assert err <= TOL_FULL_CHAIN, "max abs error %g exceeds the north_star tolerance" % err
+    assert harness.bits_equal(a, want), harness.describe_mismatch(a, want)
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_lib):
+    import torch
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_reference_golden(cuda_lib, path):
+    I, Q, ev, audio, pcm, status = load_golden(path)
+    a = harness.run_batch(cuda_lib, I, Q, ev, chunks=(5, 2, 9))
+    assert_same(a, audio)
+    p = harness.run_batch(cuda_lib, I, Q, ev, chunks=(8,), out_dtype=np.int16)
+    assert np.array_equal(p, pcm)
+
+
+@pytest.mark.parametrize("cfg,nch,nblk", [(1, 1, 345), (2, 96, 120), (3, 64, 120), (4, 140, 90), (5, 40, 120)])
+def test_cuda_matches_oracle_per_config(cuda_lib, oracle, dev, cfg, nch, nblk):
+    I, Q, ev = S.make(cfg, list(range(nch)), nblk)
+    o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
+    a, b = harness.run_batch(cuda_lib, I, Q, ev, chunks=(17, 1, 40), device=dev, return_batch=True)
+    assert_same(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+    p = harness.run_batch(cuda_lib, I, Q, ev, chunks=(64,), out_dtype=np.int16, device=dev)
+    assert np.array_equal(p, o["pcm"])
+
+
+def test_cuda_ten_seconds_usb(cuda_lib, oracle, dev):
+    """BASELINE config 1 at full length: 10 s = 3446 blocks, one USB channel, in one call."""
+    I, Q, ev = S.make(1, [0], S.BLOCKS_10S)
+    o = oracle.run(I, Q, ev)
+    a = harness.run_batch(cuda_lib, I, Q, ev, chunks=(S.BLOCKS_10S,), device=dev)
+    assert_same(a, o["audio"])
+
+
+def test_cuda_feed_forward_stage_isolation(cuda_lib, oracle, dev):
+    """Mixer + Hilbert + combine only (NB, AGC, ALS, audio filter off): north_star's 1e-6 norm-relative bar."""
+    I, Q, _ = S.make(2, list(range(8)), 60)
+    ev = []
+    for c in range(8):
+        ev += [(c, 0, "setDemodMode", [0, 1, 2, 3, 6, 1, 0, 6][c]), (c, 0, "disableNoiseBlanker"), (c, 0, "disableAGC"),
+               (c, 0, "setOutputGain", 1.0), (c, 0, "setMute", 0)]
+    o = oracle.run(I, Q, ev)
+    a = harness.run_batch(cuda_lib, I, Q, ev, chunks=(60,), device=dev)
+    peak = np.max(np.abs(o["audio"]), axis=1, keepdims=True)
+    assert np.max(np.abs(a - o["audio"]) / peak) <= 1e-6
+    assert_same(a, o["audio"])
+
+
+def test_cuda_float32_planes_and_gains(cuda_lib, oracle, dev):
+    I, Q, ev = S.make(2, list(range(40)), 30)
+    ev += [(c, 0, "setInputGain", 0.7) for c in range(0, 40, 3)] + [(c, 0, "setIQgainBalance", 1.05) for c in range(1, 40, 3)]
+    If = (I.astype(np.float32) / np.float32(32767.0)).astype(np.float32)
+    Qf = (Q.astype(np.float32) / np.float32(32767.0)).astype(np.float32)
+    o = oracle.run(If, Qf, ev, threads=4)
+    a = harness.run_batch(cuda_lib, If, Qf, ev, chunks=(4, 9), device=dev)
+    assert_same(a, o["audio"])
+    oi = oracle.run(I, Q, ev, threads=4)       # int16 wire format with non-unit gains: the reference's exact boundary
+    ai = harness.run_batch(cuda_lib, I, Q, ev, chunks=(30,), device=dev)
+    assert_same(ai, oi["audio"])
+
+
+def test_cuda_setter_fuzz(cuda_lib, oracle, dev):
+    rng = np.random.default_rng(4321)
+    I, Q, ev = S.make(4, list(range(64)), 48)
+    ev += harness.fuzz_events(rng, 64, 48, 700)
+    o = oracle.run(I, Q, ev, threads=4)
+    a = harness.run_batch(cuda_lib, I, Q, ev, chunks=(5, 2, 9), device=dev)
+    assert_same(a, o["audio"])
+    p = harness.run_batch(cuda_lib, I, Q, ev, chunks=(7,), out_dtype=np.int16, device=dev)
+    assert np.array_equal(p, o["pcm"])
+
+
+@pytest.mark.parametrize("cfg,total", [(2, 4096), (4, 16384)])
+def test_cuda_full_channel_count_sampled(cuda_lib, oracle, dev, cfg, total):
+    """BASELINE channel counts (short duration): every channel runs on the GPU, a sampled subset on the oracle."""
+    import torch
+    import audiosdr_b200 as A
+    nblk = 24
+    picks = S.sample_channels(cfg, total, 64)
+    I, Q, ev = S.make(cfg, picks, nblk)
+    o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
+    # the full batch: sampled channels carry their own signal, the rest repeat sampled rows (any valid input will do)
+    idx = np.arange(total) % len(picks)
+    pos = {c: i for i, c in enumerate(picks)}
+    for c in picks:
+        idx[c] = pos[c]
+    b = A.SdrBatch(total, _lib=cuda_lib)
+    calls = []
+    for c in range(total):
+        src = picks[idx[c]] if c not in pos else c
+        calls += [(c,) + tuple(e[2:]) for e in S.channel_events(cfg, src, 0)]
+    b.configure(calls)
+    dI = torch.from_numpy(I).to(dev)[torch.from_numpy(idx).to(dev)]
+    dQ = torch.from_numpy(Q).to(dev)[torch.from_numpy(idx).to(dev)]
+    out = torch.empty((total, nblk * 128), dtype=torch.float32, device=dev)
+    b.process(dI[:, :1280], dQ[:, :1280], out[:, :1280], n_blocks=10)
+    b.process(dI[:, 1280:].contiguous(), dQ[:, 1280:].contiguous(), out[:, 1280:], n_blocks=nblk - 10)
+    torch.cuda.synchronize()
+    res = out.cpu().numpy()
+    assert_same(res[picks], o["audio"])
+    # size-independent property: identical inputs + identical configuration => identical outputs, wherever they sit
+    assert harness.bits_equal(res, res[np.array(picks)][idx])
+
+
+def test_cuda_state_carry_long_stream_wspr(cuda_lib, oracle, dev):
+    """Config-5 style drift check, shortened: 30 s of WSPR in 23 ragged calls; last 10 s compared, plus NCO phase."""
+    nblk = 3 * S.BLOCKS_10S
+    I, Q, ev = S.make(5, [0, 1, 2, 262143], nblk)
+    o = oracle.run(I, Q, ev, threads=4)
+    a, b = harness.run_batch(cuda_lib, I, Q, ev, chunks=(449, 450, 451), device=dev, return_batch=True)
+    assert_same(a[:, -S.BLOCKS_10S * 128:], o["audio"][:, -S.BLOCKS_10S * 128:])
+    assert_same(a, o["audio"])
+    ch = oracle.Channel()
+    for e in [e for e in ev if e[0] == 0]:
+        ch.apply(e[2], *e[3:])
+    for k in range(40):
+        ch.update(I[0, k * 128:(k + 1) * 128], Q[0, k * 128:(k + 1) * 128])
+    b2 = harness.run_batch(cuda_lib, I[:1, :40 * 128], Q[:1, :40 * 128], [e for e in ev if e[0] == 0], chunks=(40,), device=dev,
+                           return_batch=True)[1]
+    assert np.float32(b2.peek_state(0, 80)) == np.float32(ch.phases()[0])  # W_PH_SSB
+
+
+def test_cuda_errors_and_launch_count(cuda_lib, dev):
+    import torch
+    import audiosdr_b200 as A
+    b = A.SdrBatch(5, _lib=cuda_lib)
+    with pytest.raises(A.SdrError):
+        b.setDemodMode(0, 7)
+    x = torch.zeros((5, 256), dtype=torch.float32, device=dev)
+    y = torch.empty_like(x)
+    n0 = b.launch_count
+    b.process(x, x, y)
+    assert b.launch_count > n0
+    with pytest.raises(A.SdrError):
+        b.process(x[:, 1:129], x[:, 1:129], y[:, :128], n_blocks=1)  # misaligned rows
+    torch.cuda.synchronize()
+    assert float(y.abs().max()) == 0.0  # silence in, silence out (NB on: zeros through the delay line)
