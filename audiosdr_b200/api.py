@@ -28,7 +28,7 @@ SETTERS = dict(
 
 EXPORTS = ["sdr_batch_create", "sdr_batch_destroy", "sdr_batch_set", "sdr_batch_configure", "sdr_batch_process_device",
            "sdr_batch_process_host", "sdr_batch_get_status", "sdr_batch_get_agc_lookup", "sdr_batch_peek_state",
-           "sdr_batch_launch_count", "sdr_batch_last_error", "sdr_batch_version"]
+           "sdr_batch_get_role_profile", "sdr_batch_launch_count", "sdr_batch_last_error", "sdr_batch_version"]
 
 
 class SdrError(RuntimeError):
@@ -71,6 +71,7 @@ def _bind(L):
     L.sdr_batch_get_status.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_get_agc_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_peek_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+    L.sdr_batch_get_role_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sdr_batch_launch_count.argtypes = [C.c_void_p]
     L.sdr_batch_launch_count.restype = C.c_uint64
     L.sdr_batch_last_error.restype = C.c_char_p
@@ -206,6 +207,19 @@ class SdrBatch:
         v = C.c_float()
         self._check(self.L.sdr_batch_peek_state(self.h, int(channel), int(word), C.byref(v)))
         return v.value
+
+    def role_profile(self):
+        """Per-stage busy fraction of the pipeline kernel (needs SDR_ROLE_PROFILE=1 at construction)."""
+        busy = np.zeros(22, np.uint64); total = np.zeros(2, np.uint64); groups = np.zeros(2, np.uint64)
+        self._check(self.L.sdr_batch_get_role_profile(self.h, busy.ctypes.data, total.ctypes.data, groups.ctypes.data))
+        names = [["in_nb", "if_i", "if_q", "nco", "hil0", "hil1", "hil2", "hil3", "aud", "agc", "als_out"],
+                 ["in_nb", "if_i", "if_q", "pll", "nco2", "img_i", "img_q", "mag", "aud", "agc", "als_out"]]
+        out = {}
+        for cls, cname in enumerate(("ssb", "env")):
+            if total[cls]:
+                out[cname] = {n: float(busy[cls * 11 + w]) / float(total[cls]) for w, n in enumerate(names[cls])}
+                out[cname]["cta_cycles_per_launch"] = float(total[cls]) / float(groups[cls])
+        return out
 
     @property
     def launch_count(self):

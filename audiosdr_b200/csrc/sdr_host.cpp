@@ -136,6 +136,8 @@ struct sdr_batch {
   float *d_gather; uint32_t *d_gather_ids; uint32_t *d_gather_words; size_t gather_cap;
   void *d_in_i, *d_in_q, *d_out; size_t stage_in_bytes, stage_out_bytes;
   uint32_t n_groups;
+  unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
+  std::vector<uint64_t> prof_busy, prof_total, prof_groups; /* folded per class */
   uint64_t blocks_done, launches;
   void *last_stream;
   std::vector<SdrChanCfg> h_cfg;
@@ -297,6 +299,8 @@ void build_groups(sdr_batch *h) {
   h->n_groups = (uint32_t)h->h_groups.size();
 }
 
+int fold_profile(sdr_batch *h);
+
 int sync_config(sdr_batch *h, void *stream) {
   if (h->luts_dirty) {
     size_t need = h->luts.size() * sizeof(float);
@@ -316,6 +320,7 @@ int sync_config(sdr_batch *h, void *stream) {
     h->groups_dirty = true; /* group feature summaries depend on the flags */
   }
   if (h->groups_dirty) {
+    if (h->prof_on && fold_profile(h)) return SDR_ERR_CUDA; /* rows are per group: fold before the grouping changes */
     build_groups(h);
     for (SdrGroup &g : h->h_groups) { g.feat = 0; for (int l = 0; l < SDR_LANES; l++) if (g.cid[l] >= 0) g.feat |= h->h_cfg[g.cid[l]].flags; }
     size_t need = sizeof(SdrGroup) * std::max<size_t>(h->h_groups.size(), 1);
@@ -350,6 +355,24 @@ int sync_config(sdr_batch *h, void *stream) {
   return 0;
 }
 
+/* fold the per-group profile rows into the per-class sums and clear the device buffer */
+int fold_profile(sdr_batch *h) {
+  if (!h->d_prof || !h->prof_launches) return 0;
+  if (dev_sync(h->last_stream)) return SDR_ERR_CUDA;
+  std::vector<unsigned long long> rows((size_t)h->n_groups * SDR_PROF_SLOTS);
+  if (rows.empty()) return 0;
+  if (d2h(rows.data(), h->d_prof, rows.size() * 8, h->last_stream) || dev_sync(h->last_stream)) return SDR_ERR_CUDA;
+  for (uint32_t g = 0; g < h->n_groups && g < h->h_groups.size(); g++) {
+    int cls = h->h_groups[g].cls;
+    for (int w = 0; w < 11; w++) h->prof_busy[cls * 11 + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
+    h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + SDR_PROF_SLOTS - 1];
+    h->prof_groups[cls] += h->prof_launches;
+  }
+  if (dev_zero(h->d_prof, rows.size() * 8, h->last_stream)) return SDR_ERR_CUDA;
+  h->prof_launches = 0;
+  return 0;
+}
+
 int check_plane(const void *p, size_t pitch, int fmt, uint32_t n_blocks, const char *what) {
   if (!p) return fail(SDR_ERR_ARG, std::string(what) + ": null plane");
   if (fmt != SDR_FMT_I16 && fmt != SDR_FMT_F32) return fail(SDR_ERR_ARG, std::string(what) + ": unknown format");
@@ -379,7 +402,7 @@ void sdr_batch_destroy(sdr_batch_t *h) {
   dev_sync(h->last_stream);
   dev_free(h->d_state); dev_free(h->d_cfg); dev_free(h->d_groups); dev_free(h->d_luts); dev_free(h->d_tabs);
   dev_free(h->d_reset_ch); dev_free(h->d_reset_mask); dev_free(h->d_gather); dev_free(h->d_gather_ids); dev_free(h->d_gather_words);
-  dev_free(h->d_in_i); dev_free(h->d_in_q); dev_free(h->d_out);
+  dev_free(h->d_in_i); dev_free(h->d_in_q); dev_free(h->d_out); dev_free(h->d_prof);
   delete h;
 }
 
@@ -397,6 +420,9 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->d_gather = nullptr; h->d_gather_ids = h->d_gather_words = nullptr; h->gather_cap = 0;
   h->d_in_i = h->d_in_q = h->d_out = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0;
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
+  h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
+  { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
+  h->prof_busy.assign(22, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
   SdrTables *t = new SdrTables();
   const uint32_t *ifs[4] = {SDR_TAB_IF_SSB, SDR_TAB_IF_CW, SDR_TAB_IF_WSPR, SDR_TAB_IF_AM};
@@ -474,6 +500,15 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
   L.n_tiles = n_blocks * SDR_TPB; L.blk0_mod3 = (uint32_t)(h->blocks_done % 3);
   L.cfg = h->d_cfg; L.state = h->d_state; L.ch_stride = h->ch_stride; L.groups = h->d_groups; L.agc_luts = h->d_luts; L.tabs = h->d_tabs;
   L.n_groups = h->n_groups;
+  if (h->prof_on) {
+    size_t need = (size_t)std::max<uint32_t>(h->n_groups, 1) * SDR_PROF_SLOTS * 8;
+    if (need > h->prof_cap) {
+      dev_free(h->d_prof); h->d_prof = nullptr;
+      if (dev_alloc((void **)&h->d_prof, need) || dev_zero(h->d_prof, need, stream)) return SDR_ERR_NOMEM;
+      h->prof_cap = need;
+    }
+    L.prof = h->d_prof; h->prof_launches++;
+  }
   int e = sdrk_launch_pipeline(&L, stream);
   if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
   h->launches++;
@@ -561,6 +596,15 @@ int sdr_batch_get_status(sdr_batch_t *h, const uint32_t *ids, uint32_t n, sdr_ch
     o.agc_enabled = s.agc_on; o.nb_enabled = s.nb_on; o.als_enabled = s.als_on; o.als_notch = s.als_notch; o.als_adaptive = s.als_adapt;
     o.audio_filter_enabled = s.aud_on;
   }
+  return SDR_OK;
+}
+
+int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy22, uint64_t *total2, uint64_t *groups2) {
+  if (!h || !busy22 || !total2 || !groups2) return fail(SDR_ERR_ARG, "get_role_profile: bad arguments");
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  if (fold_profile(h)) return SDR_ERR_CUDA;
+  for (int i = 0; i < 22; i++) busy22[i] = h->prof_busy[i];
+  for (int i = 0; i < 2; i++) { total2[i] = h->prof_total[i]; groups2[i] = h->prof_groups[i]; }
   return SDR_OK;
 }
 

@@ -15,89 +15,87 @@ using namespace sdrk;
 __constant__ float c_hilbert[64]; /* compact Hilbert half, H:757-774: constant-bank operands of the unrolled FIR */
 
 template <class Body>
-__device__ __forceinline__ void pipeline_loop(uint32_t n_tiles, int delay, int dmax, Body body) {
+__device__ __forceinline__ void pipeline_loop(const Ctx &x, uint32_t n_tiles, int delay, int dmax, Body body) {
   __syncthreads(); /* histories and tables are in shared memory */
   const uint32_t steps = n_tiles + (uint32_t)dmax;
+  unsigned long long *prof = x.L->prof;
+  long long busy = 0, t_begin = prof ? clock64() : 0;
+#pragma unroll 1
   for (uint32_t s = 0; s < steps; s++) {
     const long long tau = (long long)s - delay;
-    if (tau >= 0 && tau < (long long)n_tiles) body((uint32_t)tau);
+    if (tau >= 0 && tau < (long long)n_tiles) {
+      const long long t0 = prof ? clock64() : 0;
+      body((uint32_t)tau);
+      if (prof) busy += clock64() - t0;
+    }
     __syncthreads();
   }
-}
-
-__device__ __forceinline__ void run_ssb(const Ctx &x, int warp, int lane) {
-  const uint32_t n = x.L->n_tiles;
-  switch (warp) {
-    case 0: { RoleIn r; r.load(x, lane); pipeline_loop(n, D_IN, D_SSB_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
-    case 1: case 2: {
-      const int rail = warp - 1;
-      RoleBiquad r; r.load(x, lane, 0, rail);
-      pipeline_loop(n, D_IF, D_SSB_MAX, [&](uint32_t t) { r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true); });
-      r.save(x, 0, rail);
-    } break;
-    case 3: { RoleNco r; r.load(x, lane); pipeline_loop(n, D_NCO, D_SSB_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
-    case 4: case 5: case 6: case 7: {
-      const int sub = warp - 4;
-      RoleHilbert r; r.load(x, lane, sub);
-      pipeline_loop(n, D_HIL, D_SSB_MAX, [&](uint32_t t) { r.step(x, c_hilbert, lane, sub, t); });
-      r.save(x, lane, sub);
-    } break;
-    case 8: {
-      RoleBiquad r; r.load(x, lane, 1, 0);
-      pipeline_loop(n, D_AUD, D_SSB_MAX, [&](uint32_t t) { r.step(x.tile(S_A, t & 1), x.tile(S_B, t & 1), lane, r.on); });
-      r.save(x, 1, 0);
-    } break;
-    case 9: {
-      RoleAgc r; r.load(x, lane);
-      pipeline_loop(n, D_AGC, D_SSB_MAX, [&](uint32_t t) { r.step(x.tile(S_B, t & 1), x.tile(S_C, t % NC), lane, 0.0f); });
-      r.save(x);
-    } break;
-    default: {
-      RoleOut r; r.load(x, lane, S_C, S_ALSC);
-      pipeline_loop(n, D_OUT, D_SSB_MAX, [&](uint32_t t) { r.step(x, lane, t, S_C, S_ALSC); });
-      r.save(x, lane, S_C, S_ALSC);
-    } break;
+  if (prof && (threadIdx.x & 31) == 0) {
+    unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
+    row[threadIdx.x >> 5] += (unsigned long long)busy;
+    if (threadIdx.x == 0) row[SDR_PROF_SLOTS - 1] += (unsigned long long)(clock64() - t_begin);
   }
 }
 
-__device__ __forceinline__ void run_env(const Ctx &x, int warp, int lane) {
+/* One warp = one stage.  Stages common to both pipeline classes are instantiated once (offsets and delays
+ * are run-time values) to keep the kernel's instruction footprint small: every warp runs different code, so
+ * the hot loops of all 11 stages have to share the instruction caches. */
+__device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
   const uint32_t n = x.L->n_tiles;
+  const bool ssb = x.G->cls == CLS_SSB;
+  const int dmax = ssb ? (int)D_SSB_MAX : (int)D_ENV_MAX;
   switch (warp) {
-    case 0: { RoleIn r; r.load(x, lane); pipeline_loop(n, D_IN, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case 0: { RoleIn r; r.load(x, lane); pipeline_loop(x, n, D_IN, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
     case 1: case 2: {
       const int rail = warp - 1;
       RoleBiquad r; r.load(x, lane, 0, rail);
-      pipeline_loop(n, D_IF, D_ENV_MAX, [&](uint32_t t) { r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true); });
+      pipeline_loop(x, n, D_IF, dmax, [&](uint32_t t) { r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true); });
       r.save(x, 0, rail);
     } break;
-    case 3: { RolePll r; r.load(x, lane); pipeline_loop(n, E_D_PLL, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
-    case 4: { RoleNco2 r; r.load(x, lane); pipeline_loop(n, E_D_NCO2, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
-    case 5: case 6: {
-      const int rail = warp - 5;
-      RoleBiquad r; r.load(x, lane, 2, rail);
-      pipeline_loop(n, E_D_IMG, D_ENV_MAX, [&](uint32_t t) {
-        r.step(x.tile(E_Z2, (t & 1) * 2 + rail), x.tile(E_V, (t & 1) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
-      });
-      r.save(x, 2, rail);
-    } break;
-    case 7: { RoleMag r; r.load(x, lane); pipeline_loop(n, E_D_MAG, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
     case 8: {
       RoleBiquad r; r.load(x, lane, 1, 0);
-      pipeline_loop(n, E_D_AUD, D_ENV_MAX, [&](uint32_t t) { r.step(x.tile(E_A, t & 1), x.tile(E_B, t % NB_RING), lane, r.on); });
+      const int src = ssb ? (int)S_A : (int)E_A, dst = ssb ? (int)S_B : (int)E_B, nd = ssb ? 2 : (int)NB_RING;
+      pipeline_loop(x, n, ssb ? (int)D_AUD : (int)E_D_AUD, dmax, [&](uint32_t t) { r.step(x.tile(src, t & 1), x.tile(dst, t % nd), lane, r.on); });
       r.save(x, 1, 0);
     } break;
     case 9: {
       RoleAgc r; r.load(x, lane);
-      pipeline_loop(n, E_D_AGC, D_ENV_MAX, [&](uint32_t t) {
-        r.step(x.tile(E_B, t % NB_RING), x.tile(E_C, t % NC), lane, x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane]);
+      const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? 2 : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
+      pipeline_loop(x, n, ssb ? (int)D_AGC : (int)E_D_AGC, dmax, [&](uint32_t t) {
+        const float carrier = ssb ? 0.0f : x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane];
+        r.step(x.tile(src, t % ns), x.tile(dst, t % NC), lane, carrier);
       });
       r.save(x);
     } break;
-    default: {
-      RoleOut r; r.load(x, lane, E_C, E_ALSC);
-      pipeline_loop(n, E_D_OUT, D_ENV_MAX, [&](uint32_t t) { r.step(x, lane, t, E_C, E_ALSC); });
-      r.save(x, lane, E_C, E_ALSC);
+    case 10: {
+      const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
+      RoleOut r; r.load(x, lane, oc, oa);
+      pipeline_loop(x, n, ssb ? (int)D_OUT : (int)E_D_OUT, dmax, [&](uint32_t t) { r.step(x, lane, t, oc, oa); });
+      r.save(x, lane, oc, oa);
     } break;
+    default:
+      if (ssb) {
+        if (warp == 3) { RoleNco r; r.load(x, lane); pipeline_loop(x, n, D_NCO, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else {
+          const int sub = warp - 4;
+          RoleHilbert r; r.load(x, lane, sub);
+          pipeline_loop(x, n, D_HIL, dmax, [&](uint32_t t) { r.step(x, c_hilbert, lane, sub, t); });
+          r.save(x, lane, sub);
+        }
+      } else {
+        if (warp == 3) { RolePll r; r.load(x, lane); pipeline_loop(x, n, E_D_PLL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else if (warp == 4) { RoleNco2 r; r.load(x, lane); pipeline_loop(x, n, E_D_NCO2, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else if (warp == 7) { RoleMag r; r.load(x, lane); pipeline_loop(x, n, E_D_MAG, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else {
+          const int rail = warp - 5;
+          RoleBiquad r; r.load(x, lane, 2, rail);
+          pipeline_loop(x, n, E_D_IMG, dmax, [&](uint32_t t) {
+            r.step(x.tile(E_Z2, (t & 1) * 2 + rail), x.tile(E_V, (t & 1) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
+          });
+          r.save(x, 2, rail);
+        }
+      }
+      break;
   }
 }
 
@@ -109,8 +107,7 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
   x.smem = smem;
   for (int i = threadIdx.x; i < 257; i += SDR_THREADS) x.f(S_SINE)[i] = L.tabs->sine[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (x.G->cls == CLS_SSB) run_ssb(x, warp, lane);
-  else run_env(x, warp, lane);
+  run_group(x, warp, lane);
 }
 
 /* Zero (or re-seed) state words of listed channels: the side effects of the reference setters that

@@ -106,7 +106,10 @@ typedef struct {
   const SdrTables *tabs;
   uint32_t n_groups;
   uint32_t pad;
+  unsigned long long *prof; /* optional [n_groups][SDR_PROF_SLOTS]: busy cycles per warp role + CTA total (diagnostics) */
 } SdrLaunch;
+
+#define SDR_PROF_SLOTS 12
 
 #define SDR_AGC_LUT_STRIDE 132
 

@@ -1,0 +1,39 @@
+/* tests/emu/exhaustive_lut.cpp -- TEST SCAFFOLDING.
+ * Exhaustive proof that the product's divide-free sine-table index (sdrk::lut_index, sdr_pipeline.cuh) equals the
+ * reference expression (long)(Phase * 65535.0 / twoPI) of AudioSDR.h:364 for EVERY float Phase in [0, 8),
+ * i.e. all 2^30 + 2^23*... bit patterns 0x00000000 .. 0x40FFFFFF (the oscillator only ever sees [0, 2*pi + pi/2]). */
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <thread>
+#include <vector>
+#include "../../audiosdr_b200/csrc/sdr_pipeline.cuh"
+
+int main() {
+  const uint32_t END = 0x41000000u; /* 8.0f */
+  const float two_pi = (float)(2.0 * SDR_PI_D);
+  unsigned nt = std::thread::hardware_concurrency(); if (!nt) nt = 4;
+  std::atomic<uint64_t> bad(0);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&, t]() {
+      uint64_t lo = (uint64_t)END * t / nt, hi = (uint64_t)END * (t + 1) / nt, b = 0;
+      for (uint64_t u = lo; u < hi; u++) {
+        uint32_t bits = (uint32_t)u; float ph; memcpy(&ph, &bits, 4);
+        int want = (int)((uint16_t)(long)((double)ph * 65535.0 / (double)two_pi));
+        int got = sdrk::lut_index(ph);
+        if (ph < two_pi && want != got) { if (b < 5) fprintf(stderr, "mismatch at %a: want %d got %d\n", ph, want, got); b++; }
+      }
+      bad += b;
+    });
+  for (auto &x : th) x.join();
+  uint64_t badq = 0;
+  for (int q = -32768; q <= 32767; q++) {
+    double want = (double)(float)q / 32767.0, got = sdrk::RoleIn::q15_to_double(q);
+    if (memcmp(&want, &got, 8) != 0) { if (badq < 5) fprintf(stderr, "q15 mismatch at %d: %a vs %a\n", q, want, got); badq++; }
+  }
+  bad += badq;
+  printf("checked %u floats + 65536 int16 values, mismatches %llu\n", END, (unsigned long long)bad.load());
+  return bad.load() ? 1 : 0;
+}

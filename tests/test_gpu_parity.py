@@ -24,7 +24,8 @@ def assert_same(a, want):
         nan_a, nan_w = np.isnan(a), np.isnan(want)
         assert np.array_equal(nan_a, nan_w), "NaN pattern differs"
         a = np.where(nan_a, np.float32(0), a); want = np.where(nan_w, np.float32(0), want)
-        err = float(np.max(np.abs(a.astype(np.float64) - want.astype(np.float64)))) if a.size else 0.0
+        fin = np.isfinite(a) & np.isfinite(want)  # infinities must match exactly (checked bitwise below)
+        err = float(np.max(np.abs(a[fin].astype(np.float64) - want[fin].astype(np.float64)))) if fin.any() else 0.0
         assert err <= TOL_FULL_CHAIN, "max abs error %g exceeds the north_star tolerance" % err
     assert harness.bits_equal(a, want), harness.describe_mismatch(a, want)
 
