@@ -279,6 +279,9 @@ void resolve(const Shadow &s, SdrChanCfg &c) {
 
 void build_groups(sdr_batch *h) {
   h->h_groups.clear();
+  /* Channels of one class share groups; inside a class they are ordered by mode so that the lanes of a warp
+   * mostly run the same oscillator frequency and coefficient set (channel results never depend on the grouping). */
+  static const int order[2][5] = {{SDR_LSB, SDR_USB, SDR_CW_LSB, SDR_CW_USB, SDR_WSPR}, {SDR_AM, SDR_SAM, -1, -1, -1}};
   for (int cls = 0; cls < 2; cls++) {
     SdrGroup g; int fill = 0;
     auto flush = [&]() {
@@ -286,13 +289,14 @@ void build_groups(sdr_batch *h) {
       for (int l = fill; l < SDR_LANES; l++) g.cid[l] = -1;
       h->h_groups.push_back(g); fill = 0;
     };
-    for (uint32_t c = 0; c < h->n_ch; c++) {
-      const Shadow &s = h->sh[c];
-      int k = (s.mode == SDR_AM || s.mode == SDR_SAM) ? CLS_ENV : CLS_SSB;
-      if (k != cls) continue;
-      if (!fill) { memset(&g, 0, sizeof g); g.cls = cls; }
-      g.cid[fill++] = (int32_t)c;
-      if (fill == SDR_LANES) flush();
+    for (int mi = 0; mi < 5; mi++) {
+      if (order[cls][mi] < 0) continue;
+      for (uint32_t c = 0; c < h->n_ch; c++) {
+        if (h->sh[c].mode != order[cls][mi]) continue;
+        if (!fill) { memset(&g, 0, sizeof g); g.cls = cls; }
+        g.cid[fill++] = (int32_t)c;
+        if (fill == SDR_LANES) flush();
+      }
     }
     flush();
   }
@@ -322,7 +326,20 @@ int sync_config(sdr_batch *h, void *stream) {
   if (h->groups_dirty) {
     if (h->prof_on && fold_profile(h)) return SDR_ERR_CUDA; /* rows are per group: fold before the grouping changes */
     build_groups(h);
-    for (SdrGroup &g : h->h_groups) { g.feat = 0; for (int l = 0; l < SDR_LANES; l++) if (g.cid[l] >= 0) g.feat |= h->h_cfg[g.cid[l]].flags; }
+    for (SdrGroup &g : h->h_groups) {
+      g.feat = 0;
+      for (int k = 0; k < SDR_LUT_SLOTS; k++) g.lut_ids[k] = -1;
+      for (int l = 0; l < SDR_LANES; l++) {
+        g.lut_slot[l] = 255;
+        if (g.cid[l] < 0) continue;
+        g.feat |= h->h_cfg[g.cid[l]].flags;
+        int id = h->h_cfg[g.cid[l]].agc_lut;
+        for (int k = 0; k < SDR_LUT_SLOTS; k++) {
+          if (g.lut_ids[k] == id) { g.lut_slot[l] = (uint8_t)k; break; }
+          if (g.lut_ids[k] < 0) { g.lut_ids[k] = id; g.lut_slot[l] = (uint8_t)k; break; }
+        }
+      }
+    }
     size_t need = sizeof(SdrGroup) * std::max<size_t>(h->h_groups.size(), 1);
     if (need > h->groups_cap) {
       if (h->d_groups) { if (dev_sync(h->last_stream)) return SDR_ERR_CUDA; dev_free(h->d_groups); }

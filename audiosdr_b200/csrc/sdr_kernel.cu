@@ -39,26 +39,27 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, uint32_t n_tiles, in
 
 /* One warp = one stage.  Stages common to both pipeline classes are instantiated once (offsets and delays
  * are run-time values) to keep the kernel's instruction footprint small: every warp runs different code, so
- * the hot loops of all 11 stages have to share the instruction caches. */
+ * the hot loops of all 12 stages have to share the instruction caches. */
 __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
   const uint32_t n = x.L->n_tiles;
   const bool ssb = x.G->cls == CLS_SSB;
   const int dmax = ssb ? (int)D_SSB_MAX : (int)D_ENV_MAX;
   switch (warp) {
     case 0: { RoleIn r; r.load(x, lane); pipeline_loop(x, n, D_IN, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
-    case 1: case 2: {
-      const int rail = warp - 1;
+    case 1: { RoleNb r; r.load(x, lane); pipeline_loop(x, n, D_NB, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case 2: case 3: {
+      const int rail = warp - 2;
       RoleBiquad r; r.load(x, lane, 0, rail);
       pipeline_loop(x, n, D_IF, dmax, [&](uint32_t t) { r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true); });
       r.save(x, 0, rail);
     } break;
-    case 8: {
+    case 9: {
       RoleBiquad r; r.load(x, lane, 1, 0);
       const int src = ssb ? (int)S_A : (int)E_A, dst = ssb ? (int)S_B : (int)E_B, nd = ssb ? 2 : (int)NB_RING;
       pipeline_loop(x, n, ssb ? (int)D_AUD : (int)E_D_AUD, dmax, [&](uint32_t t) { r.step(x.tile(src, t & 1), x.tile(dst, t % nd), lane, r.on); });
       r.save(x, 1, 0);
     } break;
-    case 9: {
+    case 10: {
       RoleAgc r; r.load(x, lane);
       const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? 2 : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
       pipeline_loop(x, n, ssb ? (int)D_AGC : (int)E_D_AGC, dmax, [&](uint32_t t) {
@@ -67,7 +68,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
       });
       r.save(x);
     } break;
-    case 10: {
+    case 11: {
       const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
       RoleOut r; r.load(x, lane, oc, oa);
       pipeline_loop(x, n, ssb ? (int)D_OUT : (int)E_D_OUT, dmax, [&](uint32_t t) { r.step(x, lane, t, oc, oa); });
@@ -75,19 +76,19 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     } break;
     default:
       if (ssb) {
-        if (warp == 3) { RoleNco r; r.load(x, lane); pipeline_loop(x, n, D_NCO, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        if (warp == 4) { RoleNco r; r.load(x, lane); pipeline_loop(x, n, D_NCO, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
         else {
-          const int sub = warp - 4;
+          const int sub = warp - 5;
           RoleHilbert r; r.load(x, lane, sub);
           pipeline_loop(x, n, D_HIL, dmax, [&](uint32_t t) { r.step(x, c_hilbert, lane, sub, t); });
           r.save(x, lane, sub);
         }
       } else {
-        if (warp == 3) { RolePll r; r.load(x, lane); pipeline_loop(x, n, E_D_PLL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
-        else if (warp == 4) { RoleNco2 r; r.load(x, lane); pipeline_loop(x, n, E_D_NCO2, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
-        else if (warp == 7) { RoleMag r; r.load(x, lane); pipeline_loop(x, n, E_D_MAG, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        if (warp == 4) { RolePll r; r.load(x, lane); pipeline_loop(x, n, E_D_PLL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else if (warp == 5) { RoleNco2 r; r.load(x, lane); pipeline_loop(x, n, E_D_NCO2, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else if (warp == 8) { RoleMag r; r.load(x, lane); pipeline_loop(x, n, E_D_MAG, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
         else {
-          const int rail = warp - 5;
+          const int rail = warp - 6;
           RoleBiquad r; r.load(x, lane, 2, rail);
           pipeline_loop(x, n, E_D_IMG, dmax, [&](uint32_t t) {
             r.step(x.tile(E_Z2, (t & 1) * 2 + rail), x.tile(E_V, (t & 1) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
@@ -106,6 +107,10 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
   x.G = &L.groups[blockIdx.x];
   x.smem = smem;
   for (int i = threadIdx.x; i < 257; i += SDR_THREADS) x.f(S_SINE)[i] = L.tabs->sine[i];
+  for (int i = threadIdx.x; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i += SDR_THREADS) { /* the group's AGC tables */
+    const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];
+    if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   run_group(x, warp, lane);
 }
@@ -123,7 +128,7 @@ extern "C" __global__ void sdr_reset_kernel(float *state, unsigned long long ch_
     if ((m & SDRK_R_IMG) && w >= W_IMG_I && w < W_IMG_Q + 16) z = true;
     if ((m & SDRK_R_AUD) && w >= W_AUD && w < W_AUD + 16) z = true;
     if ((m & SDRK_R_ALS) && w >= W_ALS_C && w < W_ALS_H + 128) z = true;
-    if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING + 768) z = true;
+    if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING + 1152) z = true;
     if (z) state[(size_t)w * ch_stride + c] = 0.0f;
   }
 }

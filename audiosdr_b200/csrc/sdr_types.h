@@ -46,8 +46,9 @@ enum {
   W_ALS_C = 512,     /* 128: _als_coeffs           H:202 */
   W_ALS_H = 640,     /* 128: the last 128 ALS inputs (_als_in[0..127] after the shift, H:201) */
   W_NB_MASK = 768,   /* 96 words = 384 byte codes: _mask, block slot (abs_block % 3), H:237 */
-  W_NB_RING = 864,   /* 768: _BufferI then _BufferQ, 3 block slots of 128 each, slot = abs_block % 3, H:235-236 */
-  SDR_STATE_WORDS = 1632
+  W_NB_RING = 864,   /* 3 x 384: _BufferI, _BufferQ (H:235-236) and the envelope sqrt(I^2+Q^2) of every ring sample
+                        (computed once on arrival instead of at each of its two scans), 3 block slots of 128, slot = abs_block % 3 */
+  SDR_STATE_WORDS = 2016
 };
 
 /* noise-blanker mask codes (byte) -> value; code 0 must be 1.0 so that zeroed state == initBlanker() */
@@ -76,10 +77,13 @@ typedef struct {
 /* ---- pipeline classes ---- */
 enum { CLS_SSB = 0 /* LSB USB CW_LSB CW_USB WSPR: NCO + Hilbert */, CLS_ENV = 1 /* AM SAM: PLL + envelope */ };
 
+#define SDR_LUT_SLOTS 4
 typedef struct {
   int32_t cls;
-  uint32_t feat;           /* OR of the lanes' CF_* flags */
-  int32_t cid[SDR_LANES];  /* channel id per lane, -1 = empty */
+  uint32_t feat;                 /* OR of the lanes' CF_* flags */
+  int32_t cid[SDR_LANES];        /* channel id per lane, -1 = empty */
+  int32_t lut_ids[SDR_LUT_SLOTS];/* up to 4 distinct AGC tables of this group, staged in shared memory (-1 = unused) */
+  uint8_t lut_slot[SDR_LANES];   /* per lane: slot in lut_ids, or 255 = read the table from global memory */
 } SdrGroup;
 
 /* ---- constant tables in device memory ---- */

@@ -24,95 +24,77 @@ static float g_hilbert[64];
 namespace {
 
 struct Warp {
-  int id;
-  std::vector<RoleIn> in; std::vector<RoleBiquad> bq; std::vector<RoleNco> nco; std::vector<RoleHilbert> hil;
+  std::vector<RoleIn> in; std::vector<RoleNb> nbk; std::vector<RoleBiquad> bq; std::vector<RoleNco> nco; std::vector<RoleHilbert> hil;
   std::vector<RoleAgc> agc; std::vector<RoleOut> out; std::vector<RolePll> pll; std::vector<RoleNco2> nco2; std::vector<RoleMag> mag;
 };
 
 int delay_of(int cls, int w) {
-  static const int ssb[11] = {D_IN, D_IF, D_IF, D_NCO, D_HIL, D_HIL, D_HIL, D_HIL, D_AUD, D_AGC, D_OUT};
-  static const int env[11] = {D_IN, D_IF, D_IF, E_D_PLL, E_D_NCO2, E_D_IMG, E_D_IMG, E_D_MAG, E_D_AUD, E_D_AGC, E_D_OUT};
+  static const int ssb[12] = {D_IN, D_NB, D_IF, D_IF, D_NCO, D_HIL, D_HIL, D_HIL, D_HIL, D_AUD, D_AGC, D_OUT};
+  static const int env[12] = {D_IN, D_NB, D_IF, D_IF, E_D_PLL, E_D_NCO2, E_D_IMG, E_D_IMG, E_D_MAG, E_D_AUD, E_D_AGC, E_D_OUT};
   return cls == CLS_SSB ? ssb[w] : env[w];
+}
+
+/* phase: 0 = load, 1 = step(t), 2 = save -- one dispatch table, mirroring run_group() of sdr_kernel.cu */
+void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
+  const bool ssb = x.G->cls == CLS_SSB;
+  const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
+  if (w == 0) { k.in.resize(32); RoleIn &r = k.in[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }
+  else if (w == 1) { k.nbk.resize(32); RoleNb &r = k.nbk[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }
+  else if (w == 2 || w == 3) {
+    k.bq.resize(32); RoleBiquad &r = k.bq[lane]; const int rail = w - 2;
+    if (phase == 0) r.load(x, lane, 0, rail);
+    else if (phase == 1) r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true);
+    else r.save(x, 0, rail);
+  } else if (w == 9) {
+    k.bq.resize(32); RoleBiquad &r = k.bq[lane];
+    const int src = ssb ? (int)S_A : (int)E_A, dst = ssb ? (int)S_B : (int)E_B, nd = ssb ? 2 : (int)NB_RING;
+    if (phase == 0) r.load(x, lane, 1, 0); else if (phase == 1) r.step(x.tile(src, t & 1), x.tile(dst, t % nd), lane, r.on); else r.save(x, 1, 0);
+  } else if (w == 10) {
+    k.agc.resize(32); RoleAgc &r = k.agc[lane];
+    const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? 2 : (int)NB_RING;
+    if (phase == 0) r.load(x, lane);
+    else if (phase == 1) r.step(x.tile(src, t % ns), x.tile(oc, t % NC), lane, ssb ? 0.0f : x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane]);
+    else r.save(x);
+  } else if (w == 11) {
+    k.out.resize(32); RoleOut &r = k.out[lane];
+    if (phase == 0) r.load(x, lane, oc, oa); else if (phase == 1) r.step(x, lane, t, oc, oa); else r.save(x, lane, oc, oa);
+  } else if (ssb) {
+    if (w == 4) { k.nco.resize(32); RoleNco &r = k.nco[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
+    else { k.hil.resize(32); RoleHilbert &r = k.hil[lane]; const int sub = w - 5;
+      if (phase == 0) r.load(x, lane, sub); else if (phase == 1) r.step(x, g_hilbert, lane, sub, t); else r.save(x, lane, sub); }
+  } else {
+    if (w == 4) { k.pll.resize(32); RolePll &r = k.pll[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
+    else if (w == 5) { k.nco2.resize(32); RoleNco2 &r = k.nco2[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
+    else if (w == 8) { k.mag.resize(32); RoleMag &r = k.mag[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
+    else { k.bq.resize(32); RoleBiquad &r = k.bq[lane]; const int rail = w - 6;
+      if (phase == 0) r.load(x, lane, 2, rail);
+      else if (phase == 1) r.step(x.tile(E_Z2, (t & 1) * 2 + rail), x.tile(E_V, (t & 1) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
+      else r.save(x, 2, rail); }
+  }
 }
 
 void run_group(const SdrLaunch &L, const SdrGroup &G, bool reverse) {
   std::vector<unsigned char> smem(SDR_SMEM_BYTES, 0xFF);
   Ctx x; x.L = &L; x.G = &G; x.smem = smem.data();
   for (int i = 0; i < 257; i++) x.f(S_SINE)[i] = L.tabs->sine[i];
+  for (int i = 0; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i++) {
+    const int id = G.lut_ids[i / SDR_AGC_LUT_STRIDE];
+    if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
+  }
   const int cls = G.cls;
   const uint32_t n = L.n_tiles;
   std::vector<Warp> W(SDR_WARPS);
-  /* load phase */
-  for (int w = 0; w < SDR_WARPS; w++) {
-    Warp &k = W[w]; k.id = w;
-    for (int lane = 0; lane < 32; lane++) {
-      if (w == 0) { k.in.resize(32); k.in[lane].load(x, lane); }
-      else if (w == 1 || w == 2) { k.bq.resize(32); k.bq[lane].load(x, lane, 0, w - 1); }
-      else if (w == 8) { k.bq.resize(32); k.bq[lane].load(x, lane, 1, 0); }
-      else if (w == 9) { k.agc.resize(32); k.agc[lane].load(x, lane); }
-      else if (w == 10) { k.out.resize(32); k.out[lane].load(x, lane, cls == CLS_SSB ? S_C : E_C, cls == CLS_SSB ? S_ALSC : E_ALSC); }
-      else if (cls == CLS_SSB) {
-        if (w == 3) { k.nco.resize(32); k.nco[lane].load(x, lane); }
-        else { k.hil.resize(32); k.hil[lane].load(x, lane, w - 4); }
-      } else {
-        if (w == 3) { k.pll.resize(32); k.pll[lane].load(x, lane); }
-        else if (w == 4) { k.nco2.resize(32); k.nco2[lane].load(x, lane); }
-        else if (w == 5 || w == 6) { k.bq.resize(32); k.bq[lane].load(x, lane, 2, w - 5); }
-        else { k.mag.resize(32); k.mag[lane].load(x, lane); }
-      }
-    }
-  }
+  for (int w = 0; w < SDR_WARPS; w++) for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 0, 0);
   const int dmax = cls == CLS_SSB ? D_SSB_MAX : D_ENV_MAX;
   for (uint32_t s = 0; s < n + (uint32_t)dmax; s++) {
     for (int wi = 0; wi < SDR_WARPS; wi++) {
       int w = reverse ? SDR_WARPS - 1 - wi : wi;
       long long tau = (long long)s - delay_of(cls, w);
       if (tau < 0 || tau >= (long long)n) continue;
-      uint32_t t = (uint32_t)tau;
-      Warp &k = W[w];
-      for (int lane = 0; lane < 32; lane++) {
-        if (w == 0) k.in[lane].step(x, lane, t);
-        else if (w == 1 || w == 2) k.bq[lane].step(x.tile(S_X, (t & 1) * 2 + (w - 1)), x.tile(S_Y, (t & 1) * 2 + (w - 1)), lane, true);
-        else if (cls == CLS_SSB) {
-          if (w == 3) k.nco[lane].step(x, lane, t);
-          else if (w <= 7) k.hil[lane].step(x, g_hilbert, lane, w - 4, t);
-          else if (w == 8) k.bq[lane].step(x.tile(S_A, t & 1), x.tile(S_B, t & 1), lane, k.bq[lane].on);
-          else if (w == 9) k.agc[lane].step(x.tile(S_B, t & 1), x.tile(S_C, t % NC), lane, 0.0f);
-          else k.out[lane].step(x, lane, t, S_C, S_ALSC);
-        } else {
-          if (w == 3) k.pll[lane].step(x, lane, t);
-          else if (w == 4) k.nco2[lane].step(x, lane, t);
-          else if (w == 5 || w == 6)
-            k.bq[lane].step(x.tile(E_Z2, (t & 1) * 2 + (w - 5)), x.tile(E_V, (t & 1) * 2 + (w - 5)), lane,
-                            k.bq[lane].cid >= 0 && env_flag(x, lane, t) != 0);
-          else if (w == 7) k.mag[lane].step(x, lane, t);
-          else if (w == 8) k.bq[lane].step(x.tile(E_A, t & 1), x.tile(E_B, t % NB_RING), lane, k.bq[lane].on);
-          else if (w == 9) k.agc[lane].step(x.tile(E_B, t % NB_RING), x.tile(E_C, t % NC), lane, x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane]);
-          else k.out[lane].step(x, lane, t, E_C, E_ALSC);
-        }
-      }
+      for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 1, (uint32_t)tau);
     }
   }
-  /* save phase */
-  for (int w = 0; w < SDR_WARPS; w++) {
-    Warp &k = W[w];
-    for (int lane = 0; lane < 32; lane++) {
-      if (w == 0) k.in[lane].save(x, lane);
-      else if (w == 1 || w == 2) k.bq[lane].save(x, 0, w - 1);
-      else if (w == 8) k.bq[lane].save(x, 1, 0);
-      else if (w == 9) k.agc[lane].save(x);
-      else if (w == 10) k.out[lane].save(x, lane, cls == CLS_SSB ? S_C : E_C, cls == CLS_SSB ? S_ALSC : E_ALSC);
-      else if (cls == CLS_SSB) {
-        if (w == 3) k.nco[lane].save(x);
-        else k.hil[lane].save(x, lane, w - 4);
-      } else {
-        if (w == 3) k.pll[lane].save(x);
-        else if (w == 4) k.nco2[lane].save(x);
-        else if (w == 5 || w == 6) k.bq[lane].save(x, 2, w - 5);
-        else k.mag[lane].save(x);
-      }
-    }
-  }
+  for (int w = 0; w < SDR_WARPS; w++) for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 2, 0);
 }
 
 }  // namespace
@@ -137,7 +119,7 @@ int sdrk_launch_reset(float *state, unsigned long long ch_stride, const uint32_t
       if ((m & SDRK_R_IMG) && w >= W_IMG_I && w < W_IMG_Q + 16) z = true;
       if ((m & SDRK_R_AUD) && w >= W_AUD && w < W_AUD + 16) z = true;
       if ((m & SDRK_R_ALS) && w >= W_ALS_C && w < W_ALS_H + 128) z = true;
-      if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING + 768) z = true;
+      if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING + 1152) z = true;
       if (z) state[(size_t)w * ch_stride + c] = 0.0f;
     }
   }
