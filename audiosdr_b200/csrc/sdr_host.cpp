@@ -381,7 +381,7 @@ int fold_profile(sdr_batch *h) {
   if (d2h(rows.data(), h->d_prof, rows.size() * 8, h->last_stream) || dev_sync(h->last_stream)) return SDR_ERR_CUDA;
   for (uint32_t g = 0; g < h->n_groups && g < h->h_groups.size(); g++) {
     int cls = h->h_groups[g].cls;
-    for (int w = 0; w < 11; w++) h->prof_busy[cls * 11 + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
+    for (int w = 0; w < 12; w++) h->prof_busy[cls * 12 + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
     h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + SDR_PROF_SLOTS - 1];
     h->prof_groups[cls] += h->prof_launches;
   }
@@ -439,7 +439,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
-  h->prof_busy.assign(22, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
+  h->prof_busy.assign(24, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
   SdrTables *t = new SdrTables();
   const uint32_t *ifs[4] = {SDR_TAB_IF_SSB, SDR_TAB_IF_CW, SDR_TAB_IF_WSPR, SDR_TAB_IF_AM};
@@ -616,11 +616,11 @@ int sdr_batch_get_status(sdr_batch_t *h, const uint32_t *ids, uint32_t n, sdr_ch
   return SDR_OK;
 }
 
-int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy22, uint64_t *total2, uint64_t *groups2) {
-  if (!h || !busy22 || !total2 || !groups2) return fail(SDR_ERR_ARG, "get_role_profile: bad arguments");
+int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy24, uint64_t *total2, uint64_t *groups2) {
+  if (!h || !busy24 || !total2 || !groups2) return fail(SDR_ERR_ARG, "get_role_profile: bad arguments");
   if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
   if (fold_profile(h)) return SDR_ERR_CUDA;
-  for (int i = 0; i < 22; i++) busy22[i] = h->prof_busy[i];
+  for (int i = 0; i < 24; i++) busy24[i] = h->prof_busy[i];
   for (int i = 0; i < 2; i++) { total2[i] = h->prof_total[i]; groups2[i] = h->prof_groups[i]; }
   return SDR_OK;
 }

@@ -76,7 +76,21 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     } break;
     default:
       if (ssb) {
-        if (warp == 4) { RoleNco r; r.load(x, lane); pipeline_loop(x, n, D_NCO, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        if (warp == 4) {
+          RoleNco r; r.load(x, lane);
+          { /* does every active lane run the same oscillator? then one table per tile serves the whole group */
+            const unsigned act = __ballot_sync(0xffffffffu, r.cid >= 0);
+            const int leader = act ? __ffs(act) - 1 : 0;
+            const uint32_t pb = __shfl_sync(0xffffffffu, f2u(r.phase), leader), ib = __shfl_sync(0xffffffffu, f2u(r.inc), leader);
+            r.uniform = __all_sync(0xffffffffu, r.cid < 0 || (f2u(r.phase) == pb && f2u(r.inc) == ib)) != 0;
+            if (r.uniform) { r.phase = u2f(pb); r.inc = u2f(ib); }
+          }
+          pipeline_loop(x, n, D_NCO, dmax, [&](uint32_t t) {
+            if (r.uniform) { r.table_step(x, lane); __syncwarp(); r.mix_step(x, lane, t); }
+            else r.step(x, lane, t);
+          });
+          r.save(x);
+        }
         else {
           const int sub = warp - 5;
           RoleHilbert r; r.load(x, lane, sub);

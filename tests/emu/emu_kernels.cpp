@@ -59,7 +59,24 @@ void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
     k.out.resize(32); RoleOut &r = k.out[lane];
     if (phase == 0) r.load(x, lane, oc, oa); else if (phase == 1) r.step(x, lane, t, oc, oa); else r.save(x, lane, oc, oa);
   } else if (ssb) {
-    if (w == 4) { k.nco.resize(32); RoleNco &r = k.nco[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
+    if (w == 4) {
+      k.nco.resize(32); RoleNco &r = k.nco[lane];
+      if (phase == 0) {
+        r.load(x, lane);
+        if (lane == 31) { /* the warp vote of sdr_kernel.cu, on the 32 lane objects */
+          int leader = -1;
+          for (int l = 0; l < 32; l++) if (k.nco[l].cid >= 0) { leader = l; break; }
+          bool uni = leader >= 0;
+          for (int l = 0; l < 32 && uni; l++)
+            if (k.nco[l].cid >= 0 && (f2u(k.nco[l].phase) != f2u(k.nco[leader].phase) || f2u(k.nco[l].inc) != f2u(k.nco[leader].inc))) uni = false;
+          if (const char *e = getenv("SDR_EMU_NO_UNIFORM")) if (e[0] == '1') uni = false;
+          for (int l = 0; l < 32; l++) { k.nco[l].uniform = uni; if (uni) { k.nco[l].phase = k.nco[leader].phase; k.nco[l].inc = k.nco[leader].inc; } }
+        }
+      } else if (phase == 1) {
+        if (r.uniform) { if (lane == 0) for (int l = 0; l < 32; l++) k.nco[l].table_step(x, l); r.mix_step(x, lane, t); }
+        else r.step(x, lane, t);
+      } else r.save(x);
+    }
     else { k.hil.resize(32); RoleHilbert &r = k.hil[lane]; const int sub = w - 5;
       if (phase == 0) r.load(x, lane, sub); else if (phase == 1) r.step(x, g_hilbert, lane, sub, t); else r.save(x, lane, sub); }
   } else {
