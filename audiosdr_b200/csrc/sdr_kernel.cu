@@ -44,21 +44,26 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
   const uint32_t n = x.L->n_tiles;
   const bool ssb = x.G->cls == CLS_SSB;
   const int dmax = ssb ? (int)D_SSB_MAX : (int)D_ENV_MAX;
+  /* every 4-section cascade of the chain (IF rails, audio band-pass, AM image rails) runs through this one site */
+  const bool is_if = warp == 2 || warp == 3, is_aud = warp == 9, is_img = !ssb && (warp == 6 || warp == 7);
+  if (is_if || is_aud || is_img) {
+    const int kind = is_if ? 0 : (is_aud ? 1 : 2), rail = is_if ? warp - 2 : (is_img ? warp - 6 : 0);
+    /* tile of step t: base + ((t % cycle) * per + rail) tiles */
+    const int src = is_if ? (int)S_X : (is_aud ? (ssb ? (int)S_A : (int)E_A) : (int)E_Z2);
+    const int dst = is_if ? (int)S_Y : (is_aud ? (ssb ? (int)S_B : (int)E_B) : (int)E_V);
+    const int s_per = is_aud ? 1 : 2, d_per = is_aud ? 1 : 2, s_cyc = 2, d_cyc = (is_aud && !ssb) ? (int)NB_RING : 2;
+    const int delay = is_if ? (int)D_IF : (is_aud ? (ssb ? (int)D_AUD : (int)E_D_AUD) : (int)E_D_IMG);
+    RoleBiquad r; r.load(x, lane, kind, rail);
+    pipeline_loop(x, n, delay, dmax, [&](uint32_t t) {
+      const bool run = is_if ? true : (is_aud ? r.on : (r.cid >= 0 && env_flag(x, lane, t) != 0));
+      r.step(x.tile(src, (int)(t % s_cyc) * s_per + rail), x.tile(dst, (int)(t % d_cyc) * d_per + rail), lane, run);
+    });
+    r.save(x, kind, rail);
+    return;
+  }
   switch (warp) {
     case 0: { RoleIn r; r.load(x, lane); pipeline_loop(x, n, D_IN, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
     case 1: { RoleNb r; r.load(x, lane); pipeline_loop(x, n, D_NB, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
-    case 2: case 3: {
-      const int rail = warp - 2;
-      RoleBiquad r; r.load(x, lane, 0, rail);
-      pipeline_loop(x, n, D_IF, dmax, [&](uint32_t t) { r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true); });
-      r.save(x, 0, rail);
-    } break;
-    case 9: {
-      RoleBiquad r; r.load(x, lane, 1, 0);
-      const int src = ssb ? (int)S_A : (int)E_A, dst = ssb ? (int)S_B : (int)E_B, nd = ssb ? 2 : (int)NB_RING;
-      pipeline_loop(x, n, ssb ? (int)D_AUD : (int)E_D_AUD, dmax, [&](uint32_t t) { r.step(x.tile(src, t & 1), x.tile(dst, t % nd), lane, r.on); });
-      r.save(x, 1, 0);
-    } break;
     case 10: {
       RoleAgc r; r.load(x, lane);
       const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? 2 : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
@@ -90,8 +95,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
             else r.step(x, lane, t);
           });
           r.save(x);
-        }
-        else {
+        } else {
           const int sub = warp - 5;
           RoleHilbert r; r.load(x, lane, sub);
           pipeline_loop(x, n, D_HIL, dmax, [&](uint32_t t) { r.step(x, c_hilbert, lane, sub, t); });
@@ -100,15 +104,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
       } else {
         if (warp == 4) { RolePll r; r.load(x, lane); pipeline_loop(x, n, E_D_PLL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
         else if (warp == 5) { RoleNco2 r; r.load(x, lane); pipeline_loop(x, n, E_D_NCO2, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
-        else if (warp == 8) { RoleMag r; r.load(x, lane); pipeline_loop(x, n, E_D_MAG, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
-        else {
-          const int rail = warp - 6;
-          RoleBiquad r; r.load(x, lane, 2, rail);
-          pipeline_loop(x, n, E_D_IMG, dmax, [&](uint32_t t) {
-            r.step(x.tile(E_Z2, (t & 1) * 2 + rail), x.tile(E_V, (t & 1) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
-          });
-          r.save(x, 2, rail);
-        }
+        else { RoleMag r; r.load(x, lane); pipeline_loop(x, n, E_D_MAG, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
       }
       break;
   }

@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="", help="diagnostics only: comma list of nonb,noagc,noaud,i16 (changes the workload!)")
     ap.add_argument("--role-profile", action="store_true", help="per-stage busy fractions (adds clock reads; not for headline numbers)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -227,6 +228,10 @@ def main():
         os.environ["SDR_ROLE_PROFILE"] = "1"
     b = A.SdrBatch(nch, device=local)
     b.configure(calls)
+    variant = [v for v in args.variant.split(",") if v]
+    if "nonb" in variant: b.disableNoiseBlanker(None)
+    if "noagc" in variant: b.disableAGC(None)
+    if "noaud" in variant: b.disableAudioFilter(None)
     stream = torch.cuda.current_stream()
 
     # ---- warm-up, with an untimed parity probe of sampled channels against the oracle on step 0
@@ -336,7 +341,7 @@ def main():
                                 planes="float32 channel-major in HBM", l2="inputs per step %.0f MB >> 126 MB L2, no flush needed" % (2 * nch * ns * 4 / 1e6),
                                 parallelism="channels sharded, no collective"),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_fp32=fp32, cpu_baseline=cpu,
-                    role_profile=(b.role_profile() if args.role_profile else None),
+                    role_profile=(b.role_profile() if args.role_profile else None), variant=args.variant or None,
                     parity=parity, per_launch_ms=dict(mean=float(np.mean(per_launch_ms)), min=float(np.min(per_launch_ms)), max=float(np.max(per_launch_ms))))
         print(json.dumps(line), flush=True)
     if world > 1:
