@@ -137,7 +137,7 @@ struct sdr_batch {
   void *d_in_i, *d_in_q, *d_out; size_t stage_in_bytes, stage_out_bytes;
   uint32_t n_groups;
   unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
-  std::vector<uint64_t> prof_busy, prof_total, prof_groups; /* folded per class */
+  std::vector<uint64_t> prof_busy, prof_total, prof_groups, prof_extra; /* folded per class */
   uint64_t blocks_done, launches;
   void *last_stream;
   std::vector<SdrChanCfg> h_cfg;
@@ -297,6 +297,9 @@ void build_groups(sdr_batch *h) {
         g.cid[fill++] = (int32_t)c;
         if (fill == SDR_LANES) flush();
       }
+      /* SSB class: a group never mixes modes, so that all its lanes share one oscillator (RoleNco's table path);
+       * at most 4 partly filled groups per handle */
+      if (cls == CLS_SSB) flush();
     }
     flush();
   }
@@ -382,7 +385,8 @@ int fold_profile(sdr_batch *h) {
   for (uint32_t g = 0; g < h->n_groups && g < h->h_groups.size(); g++) {
     int cls = h->h_groups[g].cls;
     for (int w = 0; w < 12; w++) h->prof_busy[cls * 12 + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
-    h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + SDR_PROF_SLOTS - 1];
+    h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + 12];
+    h->prof_extra[cls * 2] += rows[(size_t)g * SDR_PROF_SLOTS + 13]; h->prof_extra[cls * 2 + 1] += rows[(size_t)g * SDR_PROF_SLOTS + 14];
     h->prof_groups[cls] += h->prof_launches;
   }
   if (dev_zero(h->d_prof, rows.size() * 8, h->last_stream)) return SDR_ERR_CUDA;
@@ -439,7 +443,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
-  h->prof_busy.assign(24, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
+  h->prof_busy.assign(24, 0); h->prof_extra.assign(4, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
   SdrTables *t = new SdrTables();
   const uint32_t *ifs[4] = {SDR_TAB_IF_SSB, SDR_TAB_IF_CW, SDR_TAB_IF_WSPR, SDR_TAB_IF_AM};
@@ -622,6 +626,7 @@ int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy24, uint64_t *total
   if (fold_profile(h)) return SDR_ERR_CUDA;
   for (int i = 0; i < 24; i++) busy24[i] = h->prof_busy[i];
   for (int i = 0; i < 2; i++) { total2[i] = h->prof_total[i]; groups2[i] = h->prof_groups[i]; }
+  if (getenv("SDR_ROLE_PROFILE_NB")) fprintf(stderr, "[sdr] NB sub-phases (cycles): ssb scan+edge %llu, output %llu\n", (unsigned long long)h->prof_extra[0], (unsigned long long)h->prof_extra[1]);
   return SDR_OK;
 }
 

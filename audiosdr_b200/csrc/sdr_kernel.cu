@@ -33,7 +33,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, uint32_t n_tiles, in
   if (prof && (threadIdx.x & 31) == 0) {
     unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
     row[threadIdx.x >> 5] += (unsigned long long)busy;
-    if (threadIdx.x == 0) row[SDR_PROF_SLOTS - 1] += (unsigned long long)(clock64() - t_begin);
+    if (threadIdx.x == 0) row[12] += (unsigned long long)(clock64() - t_begin);
   }
 }
 
@@ -116,6 +116,7 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
   x.L = &L;
   x.G = &L.groups[blockIdx.x];
   x.smem = smem;
+  x.gidx = (int)blockIdx.x;
   for (int i = threadIdx.x; i < 257; i += SDR_THREADS) x.f(S_SINE)[i] = L.tabs->sine[i];
   for (int i = threadIdx.x; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i += SDR_THREADS) { /* the group's AGC tables */
     const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];
@@ -208,7 +209,8 @@ __global__ void __launch_bounds__(256) sdr_fp32_peak_kernel(float *out, int iter
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         if (KIND == 0) v[i] = __fmaf_rn(v[i], a, b);
-        else { v[i] = __fmul_rn(v[i], a); v[i] = __fadd_rn(v[i], b); }
+        else if (KIND == 1) { v[i] = __fmul_rn(v[i], a); v[i] = __fadd_rn(v[i], b); }
+        else v[i] = (float)__fma_rn((double)v[i], (double)a, (double)b); /* KIND 2: F2F + DFMA + F2F per element */
       }
     }
   }
@@ -231,13 +233,14 @@ extern "C" int sdrk_fp32_peak(int kind, int iters, double *lane_ips, float *ms_o
   for (int rep = 0; rep < 2; rep++) { /* first pass warms up */
     cudaEventRecord(e0);
     if (kind == 0) sdr_fp32_peak_kernel<0><<<grid, block>>>(d, iters, 0.999f, 0.001f);
-    else sdr_fp32_peak_kernel<1><<<grid, block>>>(d, iters, 0.999f, 0.001f);
+    else if (kind == 1) sdr_fp32_peak_kernel<1><<<grid, block>>>(d, iters, 0.999f, 0.001f);
+    else sdr_fp32_peak_kernel<2><<<grid, block>>>(d, iters, 0.999f, 0.001f);
     cudaEventRecord(e1);
     if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return 2; }
   }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  const double instr = (double)grid * block * (double)iters * 64.0 * (kind == 0 ? 1.0 : 2.0);
+  const double instr = (double)grid * block * (double)iters * 64.0 * (kind == 1 ? 2.0 : 1.0); /* kind 2 counts DFMAs */
   *lane_ips = instr / (ms * 1e-3);
   *ms_out = ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1);

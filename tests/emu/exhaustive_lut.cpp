@@ -28,6 +28,39 @@ int main() {
       bad += b;
     });
   for (auto &x : th) x.join();
+  /* AGC table index and int16 output truncation without FP64: every float in [0,1] / every float in (-4,4) */
+  std::atomic<uint64_t> bad2(0);
+  {
+    std::vector<std::thread> t2;
+    for (unsigned t = 0; t < nt; t++)
+      t2.emplace_back([&, t]() {
+        uint64_t b = 0;
+        const uint32_t ONE = 0x3F800000u, FOUR = 0x40800000u;
+        for (uint64_t u = (uint64_t)(ONE + 1) * t / nt; u < (uint64_t)(ONE + 1) * (t + 1) / nt; u++) {
+          uint32_t bits = (uint32_t)u; float a; memcpy(&a, &bits, 4);
+          if ((int)((double)a * 32767.0) != sdrk::RoleAgc::q15_index(a)) { if (b < 5) fprintf(stderr, "q15_index mismatch at %a\n", a); b++; }
+        }
+        for (uint64_t u = (uint64_t)FOUR * t / nt; u < (uint64_t)FOUR * (t + 1) / nt; u++) {
+          for (int sgn = 0; sgn < 2; sgn++) {
+            uint32_t bits = (uint32_t)u | (sgn ? 0x80000000u : 0u); float g; memcpy(&g, &bits, 4);
+            int want = (int)(int16_t)(int)((double)g * 32767.0);
+            if (want != sdrk::RoleOut::pcm(g)) { if (b < 5) fprintf(stderr, "pcm mismatch at %a: %d vs %d\n", g, want, sdrk::RoleOut::pcm(g)); b++; }
+          }
+        }
+        bad2 += b;
+      });
+    for (auto &x : t2) x.join();
+  }
+  bad += bad2.load();
+  /* large magnitudes and specials for pcm */
+  {
+    const float specials[] = {65535.0f, 65536.0f, 65536.5f, 65537.99f, 65538.0f, 70000.0f, 1e9f, 3e38f, -65535.9f, -65536.0f, -65537.0f, -65538.5f, -1e20f};
+    for (float g : specials) {
+      double d = (double)g * 32767.0;
+      int i = (d >= 2147483648.0 || d <= -2147483649.0) ? (int)0x80000000 : (int)d;
+      if ((int)(int16_t)i != sdrk::RoleOut::pcm(g)) { fprintf(stderr, "pcm special mismatch at %g\n", g); bad += 1; }
+    }
+  }
   uint64_t badq = 0;
   for (int q = -32768; q <= 32767; q++) {
     double want = (double)(float)q / 32767.0, got = sdrk::RoleIn::q15_to_double(q);
