@@ -386,7 +386,7 @@ int fold_profile(sdr_batch *h) {
     int cls = h->h_groups[g].cls;
     for (int w = 0; w < 12; w++) h->prof_busy[cls * 12 + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
     h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + 12];
-    h->prof_extra[cls * 2] += rows[(size_t)g * SDR_PROF_SLOTS + 13]; h->prof_extra[cls * 2 + 1] += rows[(size_t)g * SDR_PROF_SLOTS + 14];
+    for (int e = 0; e < 8; e++) h->prof_extra[cls * 8 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 13 + e];
     h->prof_groups[cls] += h->prof_launches;
   }
   if (dev_zero(h->d_prof, rows.size() * 8, h->last_stream)) return SDR_ERR_CUDA;
@@ -443,7 +443,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
-  h->prof_busy.assign(24, 0); h->prof_extra.assign(4, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
+  h->prof_busy.assign(24, 0); h->prof_extra.assign(16, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
   SdrTables *t = new SdrTables();
   const uint32_t *ifs[4] = {SDR_TAB_IF_SSB, SDR_TAB_IF_CW, SDR_TAB_IF_WSPR, SDR_TAB_IF_AM};
@@ -626,7 +626,10 @@ int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy24, uint64_t *total
   if (fold_profile(h)) return SDR_ERR_CUDA;
   for (int i = 0; i < 24; i++) busy24[i] = h->prof_busy[i];
   for (int i = 0; i < 2; i++) { total2[i] = h->prof_total[i]; groups2[i] = h->prof_groups[i]; }
-  if (getenv("SDR_ROLE_PROFILE_NB")) fprintf(stderr, "[sdr] NB sub-phases (cycles): ssb scan+edge %llu, output %llu\n", (unsigned long long)h->prof_extra[0], (unsigned long long)h->prof_extra[1]);
+  if (getenv("SDR_ROLE_PROFILE_NB") && h->prof_total[0])
+    fprintf(stderr, "[sdr] sub-phase share of CTA time: nb.scan %.3f nb.edge %.3f nb.out %.3f | in.fetch %.3f in.ringst %.3f in.env %.3f\n",
+            (double)h->prof_extra[0] / h->prof_total[0], (double)h->prof_extra[1] / h->prof_total[0], (double)h->prof_extra[2] / h->prof_total[0],
+            (double)h->prof_extra[3] / h->prof_total[0], (double)h->prof_extra[4] / h->prof_total[0], (double)h->prof_extra[5] / h->prof_total[0]);
   return SDR_OK;
 }
 

@@ -12,6 +12,9 @@ try:
     d=json.loads(open('gpurun_out/${TAG}_v_${v//,/_}.json').read().strip().splitlines()[-1])
     rp=d['role_profile']['ssb']; cyc=rp.pop('cta_cycles_per_launch')
     steps=d['config']['blocks_per_step']*4+7
+    import re
+    for l in open('gpurun_out/${TAG}_v_${v//,/_}.json'):
+        if l.startswith('[sdr]'): print('   ', l.strip())
     print('variant [%s] %.0f Msps  cycles/step %.0f  busy kcycles/tile:'%('$v',d['value'],cyc/steps), {k:round(v*cyc/steps/1000,1) for k,v in rp.items()})
 except Exception as e:
     print('variant [$v] failed', e); print(open('gpurun_out/${TAG}_v_${v//,/_}.json').read()[-600:])
