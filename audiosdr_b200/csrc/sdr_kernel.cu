@@ -139,8 +139,13 @@ extern "C" __global__ void sdr_reset_kernel(float *state, unsigned long long ch_
     if ((m & SDRK_R_IMG) && w >= W_IMG_I && w < W_IMG_Q + 16) z = true;
     if ((m & SDRK_R_AUD) && w >= W_AUD && w < W_AUD + 16) z = true;
     if ((m & SDRK_R_ALS) && w >= W_ALS_C && w < W_ALS_H + 128) z = true;
-    if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING + 1152) z = true;
+    if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING) z = true;
     if (z) state[(size_t)w * ch_stride + c] = 0.0f;
+  }
+  if (m & SDRK_R_NB) { /* the ring planes are float4 groups: group f of channel c is float4 number f*ch_stride + c */
+    float4 *ring = reinterpret_cast<float4 *>(state + (size_t)W_NB_RING * ch_stride);
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < 288; f += gridDim.x * blockDim.x)
+      ring[(size_t)f * ch_stride + c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 

@@ -136,8 +136,12 @@ int sdrk_launch_reset(float *state, unsigned long long ch_stride, const uint32_t
       if ((m & SDRK_R_IMG) && w >= W_IMG_I && w < W_IMG_Q + 16) z = true;
       if ((m & SDRK_R_AUD) && w >= W_AUD && w < W_AUD + 16) z = true;
       if ((m & SDRK_R_ALS) && w >= W_ALS_C && w < W_ALS_H + 128) z = true;
-      if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING + 1152) z = true;
+      if ((m & SDRK_R_NB) && w >= W_NB_MASK && w < W_NB_RING) z = true;
       if (z) state[(size_t)w * ch_stride + c] = 0.0f;
+    }
+    if (m & SDRK_R_NB) {
+      float4 *ring = reinterpret_cast<float4 *>(state + (size_t)W_NB_RING * ch_stride);
+      for (uint32_t f = 0; f < 288; f++) { float4 z4; z4.x = z4.y = z4.z = z4.w = 0.0f; ring[(size_t)f * ch_stride + c] = z4; }
     }
   }
   return 0;
