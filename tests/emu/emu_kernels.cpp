@@ -85,7 +85,7 @@ void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
     else if (w == 8) { k.mag.resize(32); RoleMag &r = k.mag[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
     else { k.bq.resize(32); RoleBiquad &r = k.bq[lane]; const int rail = w - 6;
       if (phase == 0) r.load(x, lane, 2, rail);
-      else if (phase == 1) r.step(x.tile(E_Z2, (t & 1) * 2 + rail), x.tile(E_V, (t & 1) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
+      else if (phase == 1) r.step(x.tile(E_Z2, (t % NZ2) * 2 + rail), x.tile(E_V, (t % NZ2) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
       else r.save(x, 2, rail); }
   }
 }
