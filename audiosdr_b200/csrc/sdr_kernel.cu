@@ -52,7 +52,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     const int src = is_if ? (int)S_X : (is_aud ? (ssb ? (int)S_A : (int)E_A) : (int)E_Z2);
     const int dst = is_if ? (int)S_Y : (is_aud ? (ssb ? (int)S_B : (int)E_B) : (int)E_V);
     const int s_per = is_aud ? 1 : 2, d_per = is_aud ? 1 : 2;
-    const int s_cyc = is_img ? (int)NZ2 : 2, d_cyc = is_img ? (int)NZ2 : ((is_aud && !ssb) ? (int)NB_RING : 2);
+    const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : 2), d_cyc = is_img ? (int)NZ2 : ((is_aud && !ssb) ? (int)NB_RING : 2);
     const int delay = is_if ? (int)D_IF : (is_aud ? (ssb ? (int)D_AUD : (int)E_D_AUD) : (int)E_D_IMG);
     RoleBiquad r; r.load(x, lane, kind, rail);
     pipeline_loop(x, n, delay, dmax, [&](uint32_t t) {

@@ -43,7 +43,7 @@ void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
   else if (w == 2 || w == 3) {
     k.bq.resize(32); RoleBiquad &r = k.bq[lane]; const int rail = w - 2;
     if (phase == 0) r.load(x, lane, 0, rail);
-    else if (phase == 1) r.step(x.tile(S_X, (t & 1) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true);
+    else if (phase == 1) r.step(x.tile(S_X, (t % NR) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true);
     else r.save(x, 0, rail);
   } else if (w == 9) {
     k.bq.resize(32); RoleBiquad &r = k.bq[lane];
