@@ -15,7 +15,7 @@ using namespace sdrk;
 __constant__ float c_hilbert[64]; /* compact Hilbert half, H:757-774: constant-bank operands of the unrolled FIR */
 
 template <class Body>
-__device__ __forceinline__ void pipeline_loop(const Ctx &x, uint32_t n_tiles, int delay, int dmax, Body body) {
+__device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n_tiles, int delay, int dmax, Body body) {
   __syncthreads(); /* histories and tables are in shared memory */
   const uint32_t steps = n_tiles + (uint32_t)dmax;
   unsigned long long *prof = x.L->prof;
@@ -32,7 +32,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, uint32_t n_tiles, in
   }
   if (prof && (threadIdx.x & 31) == 0) {
     unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
-    row[threadIdx.x >> 5] += (unsigned long long)busy;
+    row[role] += (unsigned long long)busy;
     if (threadIdx.x == 0) row[12] += (unsigned long long)(clock64() - t_begin);
   }
 }
@@ -55,7 +55,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : 2), d_cyc = is_img ? (int)NZ2 : ((is_aud && !ssb) ? (int)NB_RING : 2);
     const int delay = is_if ? (int)D_IF : (is_aud ? (ssb ? (int)D_AUD : (int)E_D_AUD) : (int)E_D_IMG);
     RoleBiquad r; r.load(x, lane, kind, rail);
-    pipeline_loop(x, n, delay, dmax, [&](uint32_t t) {
+    pipeline_loop(x, warp, n, delay, dmax, [&](uint32_t t) {
       const bool run = is_if ? true : (is_aud ? r.on : (r.cid >= 0 && env_flag(x, lane, t) != 0));
       r.step(x.tile(src, (int)(t % s_cyc) * s_per + rail), x.tile(dst, (int)(t % d_cyc) * d_per + rail), lane, run);
     });
@@ -63,12 +63,12 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     return;
   }
   switch (warp) {
-    case 0: { RoleIn r; r.load(x, lane); pipeline_loop(x, n, D_IN, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
-    case 1: { RoleNb r; r.load(x, lane); pipeline_loop(x, n, D_NB, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case 0: { RoleIn r; r.load(x, lane); pipeline_loop(x, warp, n, D_IN, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case 1: { RoleNb r; r.load(x, lane); pipeline_loop(x, warp, n, D_NB, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
     case 10: {
       RoleAgc r; r.load(x, lane);
       const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? 2 : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
-      pipeline_loop(x, n, ssb ? (int)D_AGC : (int)E_D_AGC, dmax, [&](uint32_t t) {
+      pipeline_loop(x, warp, n, ssb ? (int)D_AGC : (int)E_D_AGC, dmax, [&](uint32_t t) {
         const float carrier = ssb ? 0.0f : x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane];
         r.step(x.tile(src, t % ns), x.tile(dst, t % NC), lane, carrier);
       });
@@ -77,7 +77,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     case 11: {
       const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
       RoleOut r; r.load(x, lane, oc, oa);
-      pipeline_loop(x, n, ssb ? (int)D_OUT : (int)E_D_OUT, dmax, [&](uint32_t t) { r.step(x, lane, t, oc, oa); });
+      pipeline_loop(x, warp, n, ssb ? (int)D_OUT : (int)E_D_OUT, dmax, [&](uint32_t t) { r.step(x, lane, t, oc, oa); });
       r.save(x, lane, oc, oa);
     } break;
     default:
@@ -91,7 +91,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
             r.uniform = __all_sync(0xffffffffu, r.cid < 0 || (f2u(r.phase) == pb && f2u(r.inc) == ib)) != 0;
             if (r.uniform) { r.phase = u2f(pb); r.inc = u2f(ib); }
           }
-          pipeline_loop(x, n, D_NCO, dmax, [&](uint32_t t) {
+          pipeline_loop(x, warp, n, D_NCO, dmax, [&](uint32_t t) {
             if (r.uniform) { r.table_step(x, lane); __syncwarp(); r.mix_step(x, lane, t); }
             else r.step(x, lane, t);
           });
@@ -99,13 +99,13 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
         } else {
           const int sub = warp - 5;
           RoleHilbert r; r.load(x, lane, sub);
-          pipeline_loop(x, n, D_HIL, dmax, [&](uint32_t t) { r.step(x, c_hilbert, lane, sub, t); });
+          pipeline_loop(x, warp, n, D_HIL, dmax, [&](uint32_t t) { r.step(x, c_hilbert, lane, sub, t); });
           r.save(x, lane, sub);
         }
       } else {
-        if (warp == 4) { RolePll r; r.load(x, lane); pipeline_loop(x, n, E_D_PLL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
-        else if (warp == 5) { RoleNco2 r; r.load(x, lane); pipeline_loop(x, n, E_D_NCO2, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
-        else { RoleMag r; r.load(x, lane); pipeline_loop(x, n, E_D_MAG, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        if (warp == 4) { RolePll r; r.load(x, lane); pipeline_loop(x, warp, n, E_D_PLL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else if (warp == 5) { RoleNco2 r; r.load(x, lane); pipeline_loop(x, warp, n, E_D_NCO2, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else { RoleMag r; r.load(x, lane); pipeline_loop(x, warp, n, E_D_MAG, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
       }
       break;
   }
@@ -123,8 +123,17 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
     const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];
     if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  run_group(x, warp, lane);
+  /* Physical warp -> stage.  The warp scheduler of an SM sub-partition favours the HIGHER warp id among eligible
+   * warps (and warp id % 4 picks the sub-partition), so the latency-bound serial stages (blanker, input, AGC,
+   * output / PLL) get the highest ids and the throughput stages with plenty of independent work (the four Hilbert
+   * warps, one per sub-partition) the lowest: the serial chains issue the moment they are ready and the FIR fills
+   * every other slot.  Stage numbering (the `warp` argument of run_group): 0 IN, 1 NB, 2/3 IF-I/IF-Q,
+   * 4..8 class specific (SSB: NCO, Hilbert x4; ENV: PLL, NCO2, image I/Q, envelope), 9 audio BPF, 10 AGC, 11 ALS+OUT. */
+  const int phys = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int map_ssb[12] = {5, 6, 7, 8, 2, 3, 9, 4, 1, 0, 10, 11};
+  const int map_env[12] = {6, 7, 5, 8, 2, 3, 9, 11, 1, 0, 10, 4};
+  const int stage = x.G->cls == CLS_SSB ? map_ssb[phys] : map_env[phys];
+  run_group(x, stage, lane);
 }
 
 /* Zero (or re-seed) state words of listed channels: the side effects of the reference setters that
