@@ -130,9 +130,9 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
    * every other slot.  Stage numbering (the `warp` argument of run_group): 0 IN, 1 NB, 2/3 IF-I/IF-Q,
    * 4..8 class specific (SSB: NCO, Hilbert x4; ENV: PLL, NCO2, image I/Q, envelope), 9 audio BPF, 10 AGC, 11 ALS+OUT. */
   const int phys = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int map_ssb[12] = {5, 6, 7, 8, 2, 3, 9, 4, 1, 0, 10, 11};
-  const int map_env[12] = {6, 7, 5, 8, 2, 3, 9, 11, 1, 0, 10, 4};
-  const int stage = x.G->cls == CLS_SSB ? map_ssb[phys] : map_env[phys];
+  /* SSB: {5,6,7,8, 2,3,9,4, 1,0,10,11}   ENV: {6,7,5,8, 2,3,9,11, 1,0,10,4}   (4 bits per entry, no local array) */
+  const unsigned long long map_ssb = 0xBA0149328765ull, map_env = 0x4A01B9328576ull;
+  const int stage = (int)(((x.G->cls == CLS_SSB ? map_ssb : map_env) >> (4 * phys)) & 15);
   run_group(x, stage, lane);
 }
 
