@@ -50,9 +50,10 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     const int kind = is_if ? 0 : (is_aud ? 1 : 2), rail = is_if ? warp - 2 : (is_img ? warp - 6 : 0);
     /* tile of step t: base + ((t % cycle) * per + rail) tiles */
     const int src = is_if ? (int)S_X : (is_aud ? (ssb ? (int)S_A : (int)E_A) : (int)E_Z2);
-    const int dst = is_if ? (int)S_Y : (is_aud ? (ssb ? (int)S_B : (int)E_B) : (int)E_V);
+    const int dst = is_if ? (int)S_Y : (is_aud ? (ssb ? (int)S_B : (int)E_B) : (int)E_V); /* audio and image filters work in place */
     const int s_per = is_aud ? 1 : 2, d_per = is_aud ? 1 : 2;
-    const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : 2), d_cyc = is_img ? (int)NZ2 : ((is_aud && !ssb) ? (int)NB_RING : 2);
+    const int a_cyc = ssb ? (int)NA : (int)NB_RING;
+    const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : a_cyc), d_cyc = is_img ? (int)NZ2 : (is_aud ? a_cyc : 2);
     const int delay = is_if ? (int)D_IF : (is_aud ? (ssb ? (int)D_AUD : (int)E_D_AUD) : (int)E_D_IMG);
     RoleBiquad r; r.load(x, lane, kind, rail);
     pipeline_loop(x, warp, n, delay, dmax, [&](uint32_t t) {
@@ -63,11 +64,15 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     return;
   }
   switch (warp) {
-    case 0: { RoleIn r; r.load(x, lane); pipeline_loop(x, warp, n, D_IN, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case 0: {
+      RoleIn r; r.load(x, lane);
+      pipeline_loop(x, warp, n, D_IN, dmax, [&](uint32_t t) { r.step_a(x, lane, t); __syncwarp(); r.step_b(x, lane, t); });
+      r.save(x, lane);
+    } break;
     case 1: { RoleNb r; r.load(x, lane); pipeline_loop(x, warp, n, D_NB, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
     case 10: {
       RoleAgc r; r.load(x, lane);
-      const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? 2 : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
+      const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? (int)NA : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
       pipeline_loop(x, warp, n, ssb ? (int)D_AGC : (int)E_D_AGC, dmax, [&](uint32_t t) {
         const float carrier = ssb ? 0.0f : x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane];
         r.step(x.tile(src, t % ns), x.tile(dst, t % NC), lane, carrier);
@@ -77,7 +82,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     case 11: {
       const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
       RoleOut r; r.load(x, lane, oc, oa);
-      pipeline_loop(x, warp, n, ssb ? (int)D_OUT : (int)E_D_OUT, dmax, [&](uint32_t t) { r.step(x, lane, t, oc, oa); });
+      pipeline_loop(x, warp, n, ssb ? (int)D_OUT : (int)E_D_OUT, dmax, [&](uint32_t t) { r.step_a(x, lane, t, oc, oa); __syncwarp(); r.step_b(x, lane, t); __syncwarp(); });
       r.save(x, lane, oc, oa);
     } break;
     default:
@@ -119,6 +124,8 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
   x.smem = smem;
   x.gidx = (int)blockIdx.x;
   for (int i = threadIdx.x; i < 257; i += SDR_THREADS) x.f(S_SINE)[i] = L.tabs->sine[i];
+  if (threadIdx.x < SDR_LANES) reinterpret_cast<int *>(smem + S_CID)[threadIdx.x] = x.G->cid[threadIdx.x];
+  __syncthreads(); /* stage IN requests its first tile from load(), which needs the channel ids */
   for (int i = threadIdx.x; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i += SDR_THREADS) { /* the group's AGC tables */
     const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];
     if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];

@@ -34,11 +34,13 @@ int delay_of(int cls, int w) {
   return cls == CLS_SSB ? ssb[w] : env[w];
 }
 
-/* phase: 0 = load, 1 = step(t), 2 = save -- one dispatch table, mirroring run_group() of sdr_kernel.cu */
+/* phase: 0 = load, 1 = step(t) part A, 3 = step(t) part B (stages that exchange data between lanes run in two
+ * parts, the kernel separates them with __syncwarp()), 2 = save -- mirrors run_group() of sdr_kernel.cu */
 void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
+  if (phase == 3 && w != 0 && w != 11) return;
   const bool ssb = x.G->cls == CLS_SSB;
   const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
-  if (w == 0) { k.in.resize(32); RoleIn &r = k.in[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }
+  if (w == 0) { k.in.resize(32); RoleIn &r = k.in[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step_a(x, lane, t); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane); }
   else if (w == 1) { k.nbk.resize(32); RoleNb &r = k.nbk[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }
   else if (w == 2 || w == 3) {
     k.bq.resize(32); RoleBiquad &r = k.bq[lane]; const int rail = w - 2;
@@ -47,17 +49,17 @@ void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
     else r.save(x, 0, rail);
   } else if (w == 9) {
     k.bq.resize(32); RoleBiquad &r = k.bq[lane];
-    const int src = ssb ? (int)S_A : (int)E_A, dst = ssb ? (int)S_B : (int)E_B, nd = ssb ? 2 : (int)NB_RING;
-    if (phase == 0) r.load(x, lane, 1, 0); else if (phase == 1) r.step(x.tile(src, t & 1), x.tile(dst, t % nd), lane, r.on); else r.save(x, 1, 0);
+    const int src = ssb ? (int)S_A : (int)E_A, dst = ssb ? (int)S_B : (int)E_B, nd = ssb ? (int)NA : (int)NB_RING;
+    if (phase == 0) r.load(x, lane, 1, 0); else if (phase == 1) r.step(x.tile(src, t % nd), x.tile(dst, t % nd), lane, r.on); else r.save(x, 1, 0);
   } else if (w == 10) {
     k.agc.resize(32); RoleAgc &r = k.agc[lane];
-    const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? 2 : (int)NB_RING;
+    const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? (int)NA : (int)NB_RING;
     if (phase == 0) r.load(x, lane);
     else if (phase == 1) r.step(x.tile(src, t % ns), x.tile(oc, t % NC), lane, ssb ? 0.0f : x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane]);
     else r.save(x);
   } else if (w == 11) {
     k.out.resize(32); RoleOut &r = k.out[lane];
-    if (phase == 0) r.load(x, lane, oc, oa); else if (phase == 1) r.step(x, lane, t, oc, oa); else r.save(x, lane, oc, oa);
+    if (phase == 0) r.load(x, lane, oc, oa); else if (phase == 1) r.step_a(x, lane, t, oc, oa); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane, oc, oa);
   } else if (ssb) {
     if (w == 4) {
       k.nco.resize(32); RoleNco &r = k.nco[lane];
@@ -94,6 +96,7 @@ void run_group(const SdrLaunch &L, const SdrGroup &G, bool reverse) {
   std::vector<unsigned char> smem(SDR_SMEM_BYTES, 0xFF);
   Ctx x; x.L = &L; x.G = &G; x.smem = smem.data(); x.gidx = 0;
   for (int i = 0; i < 257; i++) x.f(S_SINE)[i] = L.tabs->sine[i];
+  for (int i = 0; i < 32; i++) reinterpret_cast<int *>(smem.data() + S_CID)[i] = G.cid[i];
   for (int i = 0; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i++) {
     const int id = G.lut_ids[i / SDR_AGC_LUT_STRIDE];
     if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
@@ -109,6 +112,7 @@ void run_group(const SdrLaunch &L, const SdrGroup &G, bool reverse) {
       long long tau = (long long)s - delay_of(cls, w);
       if (tau < 0 || tau >= (long long)n) continue;
       for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 1, (uint32_t)tau);
+      for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 3, (uint32_t)tau);
     }
   }
   for (int w = 0; w < SDR_WARPS; w++) for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 2, 0);
