@@ -341,6 +341,7 @@ int sync_config(sdr_batch *h, void *stream) {
           if (g.lut_ids[k] == id) { g.lut_slot[l] = (uint8_t)k; break; }
           if (g.lut_ids[k] < 0) { g.lut_ids[k] = id; g.lut_slot[l] = (uint8_t)k; break; }
         }
+        if (g.lut_slot[l] == 255) g.feat |= GF_LUT_GLOBAL;
       }
     }
     size_t need = sizeof(SdrGroup) * std::max<size_t>(h->h_groups.size(), 1);

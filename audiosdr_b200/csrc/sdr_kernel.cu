@@ -269,3 +269,33 @@ extern "C" int sdrk_fp32_peak(int kind, int iters, double *lane_ips, float *ms_o
   cudaFree(d);
   return 0;
 }
+
+/* ---- self-test: the batched branch-free envelope (sqrt_hack_batch) against the plain IEEE-divide form (sqrt_hack),
+ * bit for bit, over `n` float bit patterns starting at `first` with stride `step` (covers every exponent). */
+__global__ void sdr_selftest_envelope_kernel(unsigned first, unsigned step, unsigned long long n, unsigned long long *bad) {
+  unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 8ull;
+  unsigned long long local = 0;
+  for (; i < n; i += (unsigned long long)gridDim.x * blockDim.x * 8ull) {
+    float x[8], e[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = fabsf(__uint_as_float(first + (unsigned)((i + k) * step)));
+    sqrt_hack_batch<8>(x, e);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float w = sqrt_hack(x[k]);
+      const bool same = __float_as_uint(w) == __float_as_uint(e[k]) || (w != w && e[k] != e[k]);
+      if (!same) local++;
+    }
+  }
+  if (local) atomicAdd(bad, local);
+}
+
+extern "C" int sdrk_selftest_envelope(unsigned first, unsigned step, unsigned long long n, unsigned long long *mismatches) {
+  unsigned long long *d = nullptr;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return 1;
+  cudaMemset(d, 0, 8);
+  sdr_selftest_envelope_kernel<<<148 * 8, 256>>>(first, step, n, d);
+  cudaError_t e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : 2;
+}

@@ -56,7 +56,8 @@ enum { MK_ONE = 0, MK_ZERO = 1, MK_933 = 2, MK_750 = 3, MK_500 = 4, MK_250 = 5, 
 
 /* ---- per-channel device configuration (resolved on the host from the setter shadow) ---- */
 enum {
-  CF_NB = 1u, CF_AUD = 2u, CF_AGC = 4u, CF_ALS = 8u, CF_ALS_NOTCH = 16u, CF_ALS_ADAPT = 32u, CF_MUTED = 64u
+  CF_NB = 1u, CF_AUD = 2u, CF_AGC = 4u, CF_ALS = 8u, CF_ALS_NOTCH = 16u, CF_ALS_ADAPT = 32u, CF_MUTED = 64u,
+  GF_LUT_GLOBAL = 0x10000u /* group summary only: some lane's AGC table is not among the 4 staged ones */
 };
 typedef struct {
   int32_t mode;            /* SDR_LSB..SDR_WSPR */

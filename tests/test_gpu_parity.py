@@ -167,3 +167,13 @@ def test_cuda_errors_and_launch_count(cuda_lib, dev):
         b.process(x[:, 1:129], x[:, 1:129], y[:, :128], n_blocks=1)  # misaligned rows
     torch.cuda.synchronize()
     assert float(y.abs().max()) == 0.0  # silence in, silence out (NB on: zeros through the delay line)
+
+
+def test_cuda_batched_envelope_equals_ieee_divide(cuda_lib):
+    """sqrt_hack_batch (branch-free division fast path) == sqrt_hack (IEEE divide) for 2^28 bit patterns of every exponent."""
+    import ctypes as C
+    cuda_lib.sdrk_selftest_envelope.argtypes = [C.c_uint, C.c_uint, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+    for first, step, n in ((0, 16, 1 << 28), (0x3A000000, 1, 1 << 27), (0x00000000, 1, 1 << 24), (0x7F000000, 1, 1 << 24)):
+        bad = C.c_ulonglong(12345)
+        assert cuda_lib.sdrk_selftest_envelope(first, step, n, C.byref(bad)) == 0
+        assert bad.value == 0, (hex(first), step, n, bad.value)
