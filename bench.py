@@ -103,22 +103,30 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synth_planes(dev, first_channel, n_channels, n_samples, seed):
-    """Config-2 style IF signals, generated on the device (int16 I/Q + the per-channel setter lists)."""
+def synth_planes(dev, first_channel, n_channels, n_samples, seed, config_id=CONFIG_ID):
+    """IF signals of BASELINE config 2 (headline), 3 or 5 (diagnostics), generated on the device (int16 I/Q + setter lists).
+    Two complex tones per channel (the second doubles as AM side-band energy for config 3), optional keying and impulses."""
     import torch
     import signals as S
-    f = np.zeros((n_channels, 2)); amp = np.zeros((n_channels, 2)); keyed = np.zeros(n_channels, bool); off = np.zeros(n_channels, np.int64)
+    f = np.zeros((n_channels, 2)); amp = np.zeros((n_channels, 2)); keyed = np.zeros(n_channels, bool); off = np.full(n_channels, -10**9, np.int64)
     calls = []
     for r in range(n_channels):
         c = first_channel + r
-        m = S.channel_mode(CONFIG_ID, c)
-        if m in (S.LSB, S.USB):
-            f1 = 300.0 + 900.0 * S._unit(S.chash(CONFIG_ID, c, 2)); f2 = 1300.0 + 1200.0 * S._unit(S.chash(CONFIG_ID, c, 3))
+        m = S.channel_mode(config_id, c)
+        if config_id == 3:
+            df = 100.0 * S._unit(S.chash(3, c, 4)) - 50.0
+            f[r] = [6890.0 + df, 6890.0 + df + 1000.0]; amp[r] = [0.3, 0.075]
+        elif config_id == 5:
+            f[r] = [S._audio_to_if(S.WSPR, 1500.0), 0.0]; amp[r] = [0.05, 0.0]
+        elif m in (S.LSB, S.USB):
+            f1 = 300.0 + 900.0 * S._unit(S.chash(config_id, c, 2)); f2 = 1300.0 + 1200.0 * S._unit(S.chash(config_id, c, 3))
             f[r] = [S._audio_to_if(m, f1), S._audio_to_if(m, f2)]; amp[r] = [0.2, 0.2]
         else:
             f[r] = [S._audio_to_if(m, 700.0), 0.0]; amp[r] = [0.3, 0.0]; keyed[r] = True
-        off[r] = S.chash(CONFIG_ID, c, 5) % 11025
-        calls += [(r,) + tuple(e[2:]) for e in S.channel_events(CONFIG_ID, c, 0)]
+        if config_id == 2:
+            off[r] = S.chash(config_id, c, 5) % 11025
+        calls += [(r,) + tuple(e[2:]) for e in S.channel_events(config_id, c, 0)]
+    sigma = 0.05 if config_id == 5 else 0.01
     g = torch.Generator(device=dev); g.manual_seed(seed)
     I = torch.empty((n_channels, n_samples), dtype=torch.int16, device=dev)
     Q = torch.empty_like(I)
@@ -131,8 +139,8 @@ def synth_planes(dev, first_channel, n_channels, n_samples, seed):
         key = torch.where(torch.tensor(keyed[z], device=dev)[:, None], ((t[None, :] // (44100.0 / 40.0)).long() & 1) == 0, True)
         re = az[:, 0:1] * torch.cos(ph0) * key + az[:, 1:2] * torch.cos(ph1)
         im = az[:, 0:1] * torch.sin(ph0) * key + az[:, 1:2] * torch.sin(ph1)
-        re = re + 0.01 * torch.randn(re.shape, generator=g, device=dev, dtype=torch.float64)
-        im = im + 0.01 * torch.randn(im.shape, generator=g, device=dev, dtype=torch.float64)
+        re = re + sigma * torch.randn(re.shape, generator=g, device=dev, dtype=torch.float64)
+        im = im + sigma * torch.randn(im.shape, generator=g, device=dev, dtype=torch.float64)
         burst = ((t[None, :].long() - torch.tensor(off[z], device=dev)[:, None]) % 11025) < 3
         re = torch.where(burst, 0.9, re); im = torch.where(burst, 0.9, im)
         I[z] = torch.round(re.clamp(-1, 1) * 32767.0).to(torch.int16)
@@ -198,6 +206,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", type=int, default=CONFIG_ID, choices=[2, 3, 5],
+                    help="diagnostics only: BASELINE config 3 (SAM, 65536 ch) or 5 (WSPR, 32768 ch/GPU) instead of the headline config 2")
     ap.add_argument("--variant", default="", help="diagnostics only: comma list of nonb,noagc,noaud,i16 (changes the workload!)")
     ap.add_argument("--role-profile", action="store_true", help="per-stage busy fractions (adds clock reads; not for headline numbers)")
     args = ap.parse_args()
@@ -218,10 +228,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = api.load_library()
-    nch, nblk = CHANNELS_PER_GPU, args.blocks_per_step
+    cfg_id = args.workload
+    nch = {2: CHANNELS_PER_GPU, 3: 65536, 5: 32768}[cfg_id]
+    nblk = args.blocks_per_step if cfg_id == 2 else min(args.blocks_per_step, 64)
     ns = nblk * 128
     first = rank * nch
-    I16, Q16, calls = synth_planes(dev, first, nch, ns, 0x5D120002 + rank)
+    I16, Q16, calls = synth_planes(dev, first, nch, ns, 0x5D120000 + cfg_id + rank, cfg_id)
     If = (I16.to(torch.float32) / 32767.0).contiguous(); Qf = (Q16.to(torch.float32) / 32767.0).contiguous()
     out = torch.empty((nch, ns), dtype=torch.float32, device=dev)
     if args.role_profile:
@@ -237,7 +249,7 @@ def main():
     # ---- warm-up, with an untimed parity probe of sampled channels against the oracle on step 0
     import signals as S
     from oracle import oracle_lib
-    picks = sorted(set(S.sample_channels(CONFIG_ID, nch, 12, n_shards=2)))
+    picks = sorted(set(S.sample_channels(cfg_id, nch, 12, n_shards=2)))
     parity = None
     for w in range(max(args.warmup, 3)):
         b.process(If, Qf, out, n_blocks=nblk, stream=stream)
@@ -247,7 +259,7 @@ def main():
             hi, hq = If[picks].cpu().numpy(), Qf[picks].cpu().numpy()
             ev = []
             for row, c in enumerate(picks):
-                ev += S.channel_events(CONFIG_ID, first + c, row)
+                ev += S.channel_events(cfg_id, first + c, row)
             want = oracle_lib.run(hi, hq, ev, threads=os.cpu_count() or 1, want_pcm=False)["audio"]
             parity = dict(channels=len(picks), samples=int(want.size), bit_exact=bool(np.array_equal(got.view(np.uint32), want.view(np.uint32))),
                           max_abs_err=float(np.max(np.abs(got.astype(np.float64) - want))))
@@ -342,6 +354,7 @@ def main():
                                 parallelism="channels sharded, no collective"),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_fp32=fp32, cpu_baseline=cpu,
                     role_profile=(b.role_profile() if args.role_profile else None), variant=args.variant or None,
+                    diagnostic_workload=(None if cfg_id == CONFIG_ID else "BASELINE configs[%d], %d channels/GPU: NOT the headline metric" % (cfg_id - 1, nch)),
                     parity=parity, per_launch_ms=dict(mean=float(np.mean(per_launch_ms)), min=float(np.min(per_launch_ms)), max=float(np.max(per_launch_ms))))
         print(json.dumps(line), flush=True)
     if world > 1:

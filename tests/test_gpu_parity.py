@@ -102,12 +102,11 @@ def test_cuda_setter_fuzz(cuda_lib, oracle, dev):
     assert np.array_equal(p, o["pcm"])
 
 
-@pytest.mark.parametrize("cfg,total", [(2, 4096), (4, 16384)])
-def test_cuda_full_channel_count_sampled(cuda_lib, oracle, dev, cfg, total):
+@pytest.mark.parametrize("cfg,total,nblk", [(2, 4096, 24), (4, 16384, 24), (3, 65536, 16), (5, 262144, 12)])
+def test_cuda_full_channel_count_sampled(cuda_lib, oracle, dev, cfg, total, nblk):
     """BASELINE channel counts (short duration): every channel runs on the GPU, a sampled subset on the oracle."""
     import torch
     import audiosdr_b200 as A
-    nblk = 24
     picks = S.sample_channels(cfg, total, 64)
     I, Q, ev = S.make(cfg, picks, nblk)
     o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
@@ -117,16 +116,17 @@ def test_cuda_full_channel_count_sampled(cuda_lib, oracle, dev, cfg, total):
     for c in picks:
         idx[c] = pos[c]
     b = A.SdrBatch(total, _lib=cuda_lib)
+    per_pick = [[tuple(e[2:]) for e in S.channel_events(cfg, src, 0)] for src in picks]
     calls = []
     for c in range(total):
-        src = picks[idx[c]] if c not in pos else c
-        calls += [(c,) + tuple(e[2:]) for e in S.channel_events(cfg, src, 0)]
+        calls += [(c,) + e for e in per_pick[idx[c]]]
     b.configure(calls)
     dI = torch.from_numpy(I).to(dev)[torch.from_numpy(idx).to(dev)]
     dQ = torch.from_numpy(Q).to(dev)[torch.from_numpy(idx).to(dev)]
     out = torch.empty((total, nblk * 128), dtype=torch.float32, device=dev)
-    b.process(dI[:, :1280], dQ[:, :1280], out[:, :1280], n_blocks=10)
-    b.process(dI[:, 1280:].contiguous(), dQ[:, 1280:].contiguous(), out[:, 1280:], n_blocks=nblk - 10)
+    k = 5 * 128
+    b.process(dI[:, :k], dQ[:, :k], out[:, :k], n_blocks=5)
+    b.process(dI[:, k:].contiguous(), dQ[:, k:].contiguous(), out[:, k:], n_blocks=nblk - 5)
     torch.cuda.synchronize()
     res = out.cpu().numpy()
     assert_same(res[picks], o["audio"])
