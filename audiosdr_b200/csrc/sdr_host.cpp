@@ -57,6 +57,12 @@ int d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t w, size_t rows, 
 }
 int dev_sync(void *s) { CU(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
 int dev_select(int dev) { CU(cudaSetDevice(dev)); return 0; }
+int dev_stream_create(void **s) { cudaStream_t t; CU(cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking)); *s = (void *)t; return 0; }
+void dev_stream_destroy(void *s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+int dev_event_create(void **e) { cudaEvent_t t; CU(cudaEventCreateWithFlags(&t, cudaEventDisableTiming)); *e = (void *)t; return 0; }
+void dev_event_destroy(void *e) { if (e) cudaEventDestroy((cudaEvent_t)e); }
+int dev_event_record(void *e, void *s) { CU(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return 0; }
+int dev_stream_wait(void *s, void *e) { CU(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0)); return 0; }
 #else
 int dev_alloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : fail(SDR_ERR_NOMEM, "calloc"); }
 void dev_free(void *p) { free(p); }
@@ -71,6 +77,12 @@ int d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t w, size_t rows, 
 }
 int dev_sync(void *) { return 0; }
 int dev_select(int) { return 0; }
+int dev_stream_create(void **s) { *s = nullptr; return 0; }
+void dev_stream_destroy(void *) {}
+int dev_event_create(void **e) { *e = nullptr; return 0; }
+void dev_event_destroy(void *) {}
+int dev_event_record(void *, void *) { return 0; }
+int dev_stream_wait(void *, void *) { return 0; }
 #endif
 
 inline float tabf(const uint32_t *t, int i) { float f; memcpy(&f, &t[i], 4); return f; }
@@ -134,7 +146,10 @@ struct sdr_batch {
   float *d_state; SdrChanCfg *d_cfg; SdrGroup *d_groups; float *d_luts; SdrTables *d_tabs;
   uint32_t *d_reset_ch, *d_reset_mask; size_t reset_cap; size_t luts_cap; size_t groups_cap;
   float *d_gather; uint32_t *d_gather_ids; uint32_t *d_gather_words; size_t gather_cap;
-  void *d_in_i, *d_in_q, *d_out; size_t stage_in_bytes, stage_out_bytes;
+  /* host-buffer path: two staging sets and three streams so that the H2D copy of chunk k+1, the kernel of chunk k and
+   * the D2H copy of chunk k-1 overlap */
+  void *d_in_i[2], *d_in_q[2], *d_out[2]; size_t stage_in_bytes, stage_out_bytes;
+  void *s_h2d, *s_comp, *s_d2h; void *ev_h2d[2], *ev_comp[2], *ev_d2h[2];
   uint32_t n_groups;
   unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
   std::vector<uint64_t> prof_busy, prof_total, prof_groups, prof_extra; /* folded per class */
@@ -424,7 +439,12 @@ void sdr_batch_destroy(sdr_batch_t *h) {
   dev_sync(h->last_stream);
   dev_free(h->d_state); dev_free(h->d_cfg); dev_free(h->d_groups); dev_free(h->d_luts); dev_free(h->d_tabs);
   dev_free(h->d_reset_ch); dev_free(h->d_reset_mask); dev_free(h->d_gather); dev_free(h->d_gather_ids); dev_free(h->d_gather_words);
-  dev_free(h->d_in_i); dev_free(h->d_in_q); dev_free(h->d_out); dev_free(h->d_prof);
+  for (int k = 0; k < 2; k++) {
+    dev_free(h->d_in_i[k]); dev_free(h->d_in_q[k]); dev_free(h->d_out[k]);
+    dev_event_destroy(h->ev_h2d[k]); dev_event_destroy(h->ev_comp[k]); dev_event_destroy(h->ev_d2h[k]);
+  }
+  dev_stream_destroy(h->s_h2d); dev_stream_destroy(h->s_comp); dev_stream_destroy(h->s_d2h);
+  dev_free(h->d_prof);
   delete h;
 }
 
@@ -440,7 +460,8 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->d_state = nullptr; h->d_cfg = nullptr; h->d_groups = nullptr; h->d_luts = nullptr; h->d_tabs = nullptr;
   h->d_reset_ch = h->d_reset_mask = nullptr; h->reset_cap = h->luts_cap = h->groups_cap = 0;
   h->d_gather = nullptr; h->d_gather_ids = h->d_gather_words = nullptr; h->gather_cap = 0;
-  h->d_in_i = h->d_in_q = h->d_out = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0;
+  for (int k = 0; k < 2; k++) { h->d_in_i[k] = h->d_in_q[k] = h->d_out[k] = nullptr; h->ev_h2d[k] = h->ev_comp[k] = h->ev_d2h[k] = nullptr; }
+  h->s_h2d = h->s_comp = h->s_d2h = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0;
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
@@ -543,29 +564,67 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
                            size_t out_pitch, int out_fmt, uint32_t n_blocks) {
   if (!h || !I || !Q || !audio) return fail(SDR_ERR_ARG, "process_host: bad arguments");
   if (n_blocks == 0) return fail(SDR_ERR_ARG, "n_blocks == 0");
-  size_t ns = (size_t)n_blocks * SDR_BLOCK_SAMPLES;
+  if (in_fmt != SDR_FMT_I16 && in_fmt != SDR_FMT_F32) return fail(SDR_ERR_ARG, "process_host: unknown input format");
+  if (out_fmt != SDR_FMT_I16 && out_fmt != SDR_FMT_F32) return fail(SDR_ERR_ARG, "process_host: unknown output format");
+  const size_t ns = (size_t)n_blocks * SDR_BLOCK_SAMPLES;
   if (in_pitch < ns || out_pitch < ns) return fail(SDR_ERR_ARG, "pitch shorter than the call");
-  size_t ies = in_fmt == SDR_FMT_F32 ? 4 : 2, oes = out_fmt == SDR_FMT_F32 ? 4 : 2;
-  size_t in_bytes = ns * ies * h->n_ch, out_bytes = ns * oes * h->n_ch;
+  const size_t ies = in_fmt == SDR_FMT_F32 ? 4 : 2, oes = out_fmt == SDR_FMT_F32 ? 4 : 2;
   if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
-  if (in_bytes > h->stage_in_bytes) {
-    dev_sync(h->last_stream);
-    dev_free(h->d_in_i); dev_free(h->d_in_q); h->d_in_i = h->d_in_q = nullptr; h->stage_in_bytes = 0;
-    if (dev_alloc(&h->d_in_i, in_bytes) || dev_alloc(&h->d_in_q, in_bytes)) return SDR_ERR_NOMEM;
-    h->stage_in_bytes = in_bytes;
+  /* chunking along time: ~12 chunks per call, at least 16 blocks each (every chunk is one kernel launch that
+   * reloads and saves the per-channel state, so chunks should not be tiny) */
+  uint32_t chunk = (n_blocks + 11) / 12;
+  if (chunk < 16) chunk = 16;
+  if (chunk > n_blocks) chunk = n_blocks;
+  if (h->desc.max_blocks_per_call && chunk > h->desc.max_blocks_per_call) chunk = h->desc.max_blocks_per_call;
+  const size_t cs = (size_t)chunk * SDR_BLOCK_SAMPLES;
+  const size_t in_bytes = cs * ies * h->n_ch, out_bytes = cs * oes * h->n_ch;
+  if (!h->s_comp) {
+    if (dev_stream_create(&h->s_h2d) || dev_stream_create(&h->s_comp) || dev_stream_create(&h->s_d2h)) return SDR_ERR_CUDA;
+    for (int k = 0; k < 2; k++)
+      if (dev_event_create(&h->ev_h2d[k]) || dev_event_create(&h->ev_comp[k]) || dev_event_create(&h->ev_d2h[k])) return SDR_ERR_CUDA;
   }
-  if (out_bytes > h->stage_out_bytes) {
-    dev_sync(h->last_stream);
-    dev_free(h->d_out); h->d_out = nullptr; h->stage_out_bytes = 0;
-    if (dev_alloc(&h->d_out, out_bytes)) return SDR_ERR_NOMEM;
-    h->stage_out_bytes = out_bytes;
+  if (in_bytes > h->stage_in_bytes || out_bytes > h->stage_out_bytes) {
+    dev_sync(h->last_stream); dev_sync(h->s_h2d); dev_sync(h->s_comp); dev_sync(h->s_d2h);
+    for (int k = 0; k < 2; k++) {
+      if (in_bytes > h->stage_in_bytes) {
+        dev_free(h->d_in_i[k]); dev_free(h->d_in_q[k]); h->d_in_i[k] = h->d_in_q[k] = nullptr;
+        if (dev_alloc(&h->d_in_i[k], in_bytes) || dev_alloc(&h->d_in_q[k], in_bytes)) return SDR_ERR_NOMEM;
+      }
+      if (out_bytes > h->stage_out_bytes) {
+        dev_free(h->d_out[k]); h->d_out[k] = nullptr;
+        if (dev_alloc(&h->d_out[k], out_bytes)) return SDR_ERR_NOMEM;
+      }
+    }
+    if (in_bytes > h->stage_in_bytes) h->stage_in_bytes = in_bytes;
+    if (out_bytes > h->stage_out_bytes) h->stage_out_bytes = out_bytes;
   }
-  if (h2d_2d(h->d_in_i, ns * ies, I, in_pitch * ies, ns * ies, h->n_ch, nullptr)) return SDR_ERR_CUDA;
-  if (h2d_2d(h->d_in_q, ns * ies, Q, in_pitch * ies, ns * ies, h->n_ch, nullptr)) return SDR_ERR_CUDA;
-  int rc = sdr_batch_process_device(h, h->d_in_i, h->d_in_q, ns, in_fmt, h->d_out, ns, out_fmt, n_blocks, nullptr);
-  if (rc) return rc;
-  if (d2h_2d(audio, out_pitch * oes, h->d_out, ns * oes, ns * oes, h->n_ch, nullptr)) return SDR_ERR_CUDA;
-  if (dev_sync(nullptr)) return SDR_ERR_CUDA;
+  /* work queued by an earlier process_device call on another stream must finish before the state is touched here */
+  if (h->last_stream != h->s_comp && dev_sync(h->last_stream)) return SDR_ERR_CUDA;
+  uint32_t done = 0, k = 0;
+  while (done < n_blocks) {
+    const uint32_t nb = std::min(chunk, n_blocks - done);
+    const size_t w_in = (size_t)nb * SDR_BLOCK_SAMPLES * ies, w_out = (size_t)nb * SDR_BLOCK_SAMPLES * oes;
+    const int b = (int)(k & 1);
+    const char *srcI = (const char *)I + (size_t)done * SDR_BLOCK_SAMPLES * ies, *srcQ = (const char *)Q + (size_t)done * SDR_BLOCK_SAMPLES * ies;
+    char *dst = (char *)audio + (size_t)done * SDR_BLOCK_SAMPLES * oes;
+    /* H2D of chunk k into staging set b: the kernel of chunk k-2 must be done with it */
+    if (k >= 2 && dev_stream_wait(h->s_h2d, h->ev_comp[b])) return SDR_ERR_CUDA;
+    if (h2d_2d(h->d_in_i[b], cs * ies, srcI, in_pitch * ies, w_in, h->n_ch, h->s_h2d)) return SDR_ERR_CUDA;
+    if (h2d_2d(h->d_in_q[b], cs * ies, srcQ, in_pitch * ies, w_in, h->n_ch, h->s_h2d)) return SDR_ERR_CUDA;
+    if (dev_event_record(h->ev_h2d[b], h->s_h2d)) return SDR_ERR_CUDA;
+    /* kernel of chunk k: needs its input, and the D2H of chunk k-2 must have drained output set b */
+    if (dev_stream_wait(h->s_comp, h->ev_h2d[b])) return SDR_ERR_CUDA;
+    if (k >= 2 && dev_stream_wait(h->s_comp, h->ev_d2h[b])) return SDR_ERR_CUDA;
+    int rc = sdr_batch_process_device(h, h->d_in_i[b], h->d_in_q[b], cs, in_fmt, h->d_out[b], cs, out_fmt, nb, h->s_comp);
+    if (rc) return rc;
+    if (dev_event_record(h->ev_comp[b], h->s_comp)) return SDR_ERR_CUDA;
+    /* D2H of chunk k */
+    if (dev_stream_wait(h->s_d2h, h->ev_comp[b])) return SDR_ERR_CUDA;
+    if (d2h_2d(dst, out_pitch * oes, h->d_out[b], cs * oes, w_out, h->n_ch, h->s_d2h)) return SDR_ERR_CUDA;
+    if (dev_event_record(h->ev_d2h[b], h->s_d2h)) return SDR_ERR_CUDA;
+    done += nb; k++;
+  }
+  if (dev_sync(h->s_d2h) || dev_sync(h->s_comp) || dev_sync(h->s_h2d)) return SDR_ERR_CUDA;
   return SDR_OK;
 }
 

@@ -54,6 +54,9 @@ def test_cuda_matches_oracle_per_config(cuda_lib, oracle, dev, cfg, nch, nblk):
     assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
     p = harness.run_batch(cuda_lib, I, Q, ev, chunks=(64,), out_dtype=np.int16, device=dev)
     assert np.array_equal(p, o["pcm"])
+    # host-buffer entry point in one call: internally split into overlapped H2D / kernel / D2H chunks
+    hp = harness.run_batch(cuda_lib, I, Q, ev, chunks=(nblk,), out_dtype=np.int16, device=None)
+    assert np.array_equal(hp, o["pcm"])
 
 
 def test_cuda_ten_seconds_usb(cuda_lib, oracle, dev):
