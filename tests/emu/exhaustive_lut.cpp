@@ -61,6 +61,34 @@ int main() {
       if ((int)(int16_t)i != sdrk::RoleOut::pcm(g)) { fprintf(stderr, "pcm special mismatch at %g\n", g); bad += 1; }
     }
   }
+  /* float-only forms of (float)((double)x + PI/2), (float)((double)x +- PI) over their whole operand ranges, and the PLL wrap compares */
+  {
+    std::atomic<uint64_t> bad3(0);
+    std::vector<std::thread> t3;
+    for (unsigned t = 0; t < nt; t++)
+      t3.emplace_back([&, t]() {
+        uint64_t b = 0;
+        auto walk = [&](float lim, int sign, int which) {
+          uint32_t top; memcpy(&top, &lim, 4);
+          for (uint64_t u = (uint64_t)(top + 1) * t / nt; u < (uint64_t)(top + 1) * (t + 1) / nt; u++) {
+            uint32_t bits = (uint32_t)u | (sign ? 0x80000000u : 0u); float x; memcpy(&x, &bits, 4);
+            float want, got;
+            if (which == 0) { want = (float)((double)x + SDR_PI_D / 2.0); got = sdrk::add_half_pi(x); }
+            else if (which == 1) { want = (float)((double)x + SDR_PI_D); got = sdrk::add_pi(x); }
+            else { want = (float)((double)x - SDR_PI_D); got = sdrk::sub_pi(x); }
+            if (memcmp(&want, &got, 4)) { if (b < 5) fprintf(stderr, "add_dconst(%d) mismatch at %a\n", which, x); b++; }
+            if (which == 0) {
+              if (((double)x >= SDR_PI_D) != (x >= 0x1.921fb6p+1f) || ((double)x < -SDR_PI_D) != (x < -0x1.921fb4p+1f)) { if (b < 5) fprintf(stderr, "wrap compare mismatch at %a\n", x); b++; }
+            }
+          }
+        };
+        walk(6.2831860f, 0, 0); walk(3.1415930f, 1, 0);
+        walk(0.79f, 0, 1); walk(0.79f, 1, 1); walk(0.79f, 0, 2); walk(0.79f, 1, 2);
+        bad3 += b;
+      });
+    for (auto &x : t3) x.join();
+    bad += bad3.load();
+  }
   uint64_t badq = 0;
   for (int q = -32768; q <= 32767; q++) {
     double want = (double)(float)q / 32767.0, got = sdrk::RoleIn::q15_to_double(q);
