@@ -152,7 +152,7 @@ struct sdr_batch {
   void *s_h2d, *s_comp, *s_d2h; void *ev_h2d[2], *ev_comp[2], *ev_d2h[2];
   uint32_t n_groups;
   unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
-  std::vector<uint64_t> prof_busy, prof_total, prof_groups, prof_extra; /* folded per class */
+  std::vector<uint64_t> prof_busy, prof_total, prof_groups, prof_extra, prof_load; /* folded per class */
   uint64_t blocks_done, launches;
   void *last_stream;
   std::vector<SdrChanCfg> h_cfg;
@@ -403,6 +403,7 @@ int fold_profile(sdr_batch *h) {
     for (int w = 0; w < 12; w++) h->prof_busy[cls * 12 + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
     h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + 12];
     for (int e = 0; e < 8; e++) h->prof_extra[cls * 8 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 13 + e];
+    for (int e = 0; e < 13; e++) h->prof_load[cls * 13 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 24 + e];
     h->prof_groups[cls] += h->prof_launches;
   }
   if (dev_zero(h->d_prof, rows.size() * 8, h->last_stream)) return SDR_ERR_CUDA;
@@ -465,7 +466,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
-  h->prof_busy.assign(24, 0); h->prof_extra.assign(16, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
+  h->prof_busy.assign(24, 0); h->prof_extra.assign(16, 0); h->prof_load.assign(26, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
   SdrTables *t = new SdrTables();
   const uint32_t *ifs[4] = {SDR_TAB_IF_SSB, SDR_TAB_IF_CW, SDR_TAB_IF_WSPR, SDR_TAB_IF_AM};
@@ -686,6 +687,14 @@ int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy24, uint64_t *total
   if (fold_profile(h)) return SDR_ERR_CUDA;
   for (int i = 0; i < 24; i++) busy24[i] = h->prof_busy[i];
   for (int i = 0; i < 2; i++) { total2[i] = h->prof_total[i]; groups2[i] = h->prof_groups[i]; }
+  if (getenv("SDR_ROLE_PROFILE_NB"))
+    for (int cls = 0; cls < 2; cls++)
+      if (h->prof_groups[cls]) {
+        fprintf(stderr, "[sdr] class %d: cycles per CTA launch: prologue %.0f, pipeline %.0f; state-load cycles per stage:", cls,
+                (double)h->prof_load[cls * 13 + 12] / h->prof_groups[cls], (double)h->prof_total[cls] / h->prof_groups[cls]);
+        for (int w = 0; w < 12; w++) fprintf(stderr, " %.0f", (double)h->prof_load[cls * 13 + w] / h->prof_groups[cls]);
+        fprintf(stderr, "\n");
+      }
   if (getenv("SDR_ROLE_PROFILE_NB") && h->prof_total[0])
     fprintf(stderr, "[sdr] sub-phase share of CTA time: nb.scan %.3f nb.edge %.3f nb.out %.3f | in.fetch %.3f in.ringst %.3f in.env %.3f\n",
             (double)h->prof_extra[0] / h->prof_total[0], (double)h->prof_extra[1] / h->prof_total[0], (double)h->prof_extra[2] / h->prof_total[0],

@@ -16,9 +16,10 @@ __constant__ float c_hilbert[64]; /* compact Hilbert half, H:757-774: constant-b
 
 template <class Body>
 __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n_tiles, int delay, int dmax, Body body) {
+  unsigned long long *prof = x.L->prof;
+  const long long t_loaded = prof ? clock64() : 0;
   __syncthreads(); /* histories and tables are in shared memory */
   const uint32_t steps = n_tiles + (uint32_t)dmax;
-  unsigned long long *prof = x.L->prof;
   long long busy = 0, t_begin = prof ? clock64() : 0;
 #pragma unroll 1
   for (uint32_t s = 0; s < steps; s++) {
@@ -33,7 +34,8 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n
   if (prof && (threadIdx.x & 31) == 0) {
     unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
     row[role] += (unsigned long long)busy;
-    if (threadIdx.x == 0) row[12] += (unsigned long long)(clock64() - t_begin);
+    row[24 + role] += (unsigned long long)(t_loaded - x.t0);                 /* this stage's state load */
+    if (threadIdx.x == 0) { row[12] += (unsigned long long)(clock64() - t_begin); row[36] += (unsigned long long)(t_begin - x.t0); }
   }
 }
 
@@ -123,6 +125,7 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
   x.G = &L.groups[blockIdx.x];
   x.smem = smem;
   x.gidx = (int)blockIdx.x;
+  x.t0 = L.prof ? clock64() : 0;
   for (int i = threadIdx.x; i < 257; i += SDR_THREADS) x.f(S_SINE)[i] = L.tabs->sine[i];
   if (threadIdx.x < SDR_LANES) reinterpret_cast<int *>(smem + S_CID)[threadIdx.x] = x.G->cid[threadIdx.x];
   __syncthreads(); /* stage IN requests its first tile from load(), which needs the channel ids */
