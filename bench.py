@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", type=int, default=CONFIG_ID, choices=[2, 3, 5],
                     help="diagnostics only: BASELINE config 3 (SAM, 65536 ch) or 5 (WSPR, 32768 ch/GPU) instead of the headline config 2")
-    ap.add_argument("--variant", default="", help="diagnostics only: comma list of nonb,noagc,noaud,i16 (changes the workload!)")
+    ap.add_argument("--variant", default="", help="diagnostics only: comma list of nonb,noagc,noaud,als (changes the workload!)")
     ap.add_argument("--role-profile", action="store_true", help="per-stage busy fractions (adds clock reads; not for headline numbers)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -244,6 +244,7 @@ def main():
     if "nonb" in variant: b.disableNoiseBlanker(None)
     if "noagc" in variant: b.disableAGC(None)
     if "noaud" in variant: b.disableAudioFilter(None)
+    if "als" in variant: b.enableALSfilter(None)
     stream = torch.cuda.current_stream()
 
     # ---- warm-up, with an untimed parity probe of sampled channels against the oracle on step 0
