@@ -14,11 +14,19 @@ using namespace sdrk;
 
 __constant__ float c_hilbert[64]; /* compact Hilbert half, H:757-774: constant-bank operands of the unrolled FIR */
 
+/* CTA-wide step barrier.  Every warp is a different stage and reaches the barrier from a different instruction, so the
+ * unaligned form (`barrier.sync`, sm_70+) is used after re-converging the warp: lanes of an incompletely filled group
+ * leave their stage body early. */
+__device__ __forceinline__ void step_barrier() {
+  __syncwarp();
+  asm volatile("barrier.sync 0;" ::: "memory");
+}
+
 template <class Body>
 __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n_tiles, int delay, int dmax, Body body) {
   unsigned long long *prof = x.L->prof;
   const long long t_loaded = prof ? clock64() : 0;
-  __syncthreads(); /* histories and tables are in shared memory */
+  step_barrier(); /* histories and tables are in shared memory */
   const uint32_t steps = n_tiles + (uint32_t)dmax;
   long long busy = 0, t_begin = prof ? clock64() : 0;
 #pragma unroll 1
@@ -29,7 +37,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n
       body((uint32_t)tau);
       if (prof) busy += clock64() - t0;
     }
-    __syncthreads();
+    step_barrier();
   }
   if (prof && (threadIdx.x & 31) == 0) {
     unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;

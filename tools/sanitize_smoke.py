@@ -1,0 +1,16 @@
+"""tools/sanitize_smoke.py -- tiny all-mode run for compute-sanitizer (memcheck / racecheck / initcheck / synccheck)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import harness, signals as S
+from audiosdr_b200 import api
+from oracle import oracle_lib
+lib = api.load_library()
+I, Q, ev = S.make(4, list(range(70)), 6)
+want = oracle_lib.run(I, Q, ev, threads=4)
+got = harness.run_batch(lib, I, Q, ev, chunks=(2, 4), device=torch.device("cuda:0"))
+assert np.array_equal(got.view(np.uint32), want["audio"].view(np.uint32))
+pcm = harness.run_batch(lib, I, Q, ev, chunks=(6,), out_dtype=np.int16, device=None)
+assert np.array_equal(pcm, want["pcm"])
+print("sanitize smoke ok")
