@@ -180,3 +180,44 @@ def test_cuda_batched_envelope_equals_ieee_divide(cuda_lib):
         bad = C.c_ulonglong(12345)
         assert cuda_lib.sdrk_selftest_envelope(first, step, n, C.byref(bad)) == 0
         assert bad.value == 0, (hex(first), step, n, bad.value)
+
+
+def test_cuda_ragged_shapes_and_pitches(cuda_lib, oracle, dev):
+    """Edge cases: 1 and 33 channels (partly filled groups), one block per call, row pitch larger than the call,
+    planes that are views into a bigger buffer, int16 in / float32 out and the reverse."""
+    import torch
+    import audiosdr_b200 as A
+    for nch in (1, 33):
+        I, Q, ev = S.make(4, list(range(5, 5 + nch)), 9)
+        o = oracle.run(I, Q, ev, threads=2)
+        b = A.SdrBatch(nch, _lib=cuda_lib)
+        b.configure([(e[0], e[2]) + tuple(e[3:]) for e in ev])
+        big_i = torch.zeros((nch, 9 * 128 + 256), dtype=torch.int16, device=dev)
+        big_q = torch.zeros_like(big_i)
+        big_i[:, 128:128 + 9 * 128] = torch.from_numpy(I).to(dev)
+        big_q[:, 128:128 + 9 * 128] = torch.from_numpy(Q).to(dev)
+        out = torch.full((nch, 9 * 128 + 64), 7.0, dtype=torch.float32, device=dev)
+        for k in range(9):  # one block per call, views with offset 128 samples (256 B: still 16-byte aligned) and long pitch
+            a = 128 + k * 128
+            b.process(big_i[:, a:a + 128], big_q[:, a:a + 128], out[:, k * 128:(k + 1) * 128], n_blocks=1)
+        torch.cuda.synchronize()
+        res = out.cpu().numpy()
+        assert_same(res[:, :9 * 128], o["audio"])
+        assert np.all(res[:, 9 * 128:] == 7.0)  # nothing written past the call
+    # float32 in / int16 out
+    I, Q, ev = S.make(2, list(range(40)), 16)
+    If = (I.astype(np.float32) / np.float32(32767.0)).astype(np.float32); Qf = (Q.astype(np.float32) / np.float32(32767.0)).astype(np.float32)
+    o = oracle.run(If, Qf, ev, threads=4)
+    p = harness.run_batch(cuda_lib, If, Qf, ev, chunks=(16,), out_dtype=np.int16, device=dev)
+    assert np.array_equal(p, o["pcm"])
+
+
+def test_cuda_large_single_call(cuda_lib, oracle, dev):
+    """A long single call (BASELINE's 10 s = 3446 blocks) on a few mixed channels, and the same stream cut into
+    1-block calls: identical bits (state carry through HBM at every call boundary)."""
+    I, Q, ev = S.make(4, list(range(14)), 800)
+    o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
+    a = harness.run_batch(cuda_lib, I, Q, ev, chunks=(800,), device=dev)
+    assert_same(a, o["audio"])
+    b = harness.run_batch(cuda_lib, I[:, :60 * 128], Q[:, :60 * 128], ev, chunks=(1,), device=dev)
+    assert_same(b, o["audio"][:, :60 * 128])
