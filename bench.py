@@ -174,6 +174,17 @@ def cpu_reference_rate(seconds, cores):
     return dict(value=total / busy / 1e6, unit=UNIT, cores=cores, kind="port", sample=sample)
 
 
+WORKLOAD = "BASELINE configs[1]: 4096 channels/GPU, mixed CW_LSB/CW_USB/LSB/USB, NB(10 dB)+AGC(medium)+audio BPF"
+
+
+def config_dict(nch, nblk):
+    ns = nblk * 128
+    return dict(workload=WORKLOAD, channels_per_gpu=nch, blocks_per_step=nblk, samples_per_step=int(nch) * ns,
+                planes="float32 channel-major in HBM",
+                l2="inputs per step %.0f MB >> 126 MB L2, no flush needed" % (2 * nch * ns * 4 / 1e6),
+                parallelism="channels sharded, no collective")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -190,8 +201,9 @@ def run_reference(args, rank, world):
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=float(np.mean(t_steps)), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="BASELINE configs[1]: mixed CW/LSB/USB channels, NB+AGC+audio BPF; reference update() on host CPU",
-                            channels=r["cores"], step="%.0f s of streaming per step" % per_step),
+                config=dict(config_dict(CHANNELS_PER_GPU, args.blocks_per_step),
+                            reference_arm="unmodified reference update() on the host CPU, %d workers, each step = %.0f s of streaming over "
+                                          "sampled channels of this workload" % (r["cores"], per_step)),
                 cpu_baseline=r, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -349,10 +361,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=cnt["max_ms"] / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                     data="synthetic",
-                    config=dict(workload="BASELINE configs[1]: 4096 channels/GPU, mixed CW_LSB/CW_USB/LSB/USB, NB(10 dB)+AGC(medium)+audio BPF",
-                                channels_per_gpu=nch, blocks_per_step=nblk, samples_per_step=int(samples_per_launch),
-                                planes="float32 channel-major in HBM", l2="inputs per step %.0f MB >> 126 MB L2, no flush needed" % (2 * nch * ns * 4 / 1e6),
-                                parallelism="channels sharded, no collective"),
+                    config=config_dict(nch, nblk),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_fp32=fp32, cpu_baseline=cpu,
                     role_profile=(b.role_profile() if args.role_profile else None), variant=args.variant or None,
                     diagnostic_workload=(None if cfg_id == CONFIG_ID else "BASELINE configs[%d], %d channels/GPU: NOT the headline metric" % (cfg_id - 1, nch)),
