@@ -27,6 +27,13 @@ try:
     d=json.loads(open('gpurun_out/${TAG}_diag_w$w.json').read().strip().splitlines()[-1]); print('workload $w:', round(d['value']), 'Msps', d['parity'], {k:{kk:round(vv,3) for kk,vv in v.items()} for k,v in (d['role_profile'] or {}).items()})
 except Exception as e: print('diag failed', e); print(open('gpurun_out/${TAG}_diag_w$w.err').read()[-500:])"
 done
+echo "== compute-sanitizer (all-mode smoke case)"
+for t in memcheck racecheck synccheck initcheck; do
+  timeout 420 compute-sanitizer --tool $t --kernel-name kernel_substring=sdr_ --print-limit 3 python tools/sanitize_smoke.py > gpurun_out/${TAG}_sanitize_$t.log 2>&1
+  echo "$t rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/${TAG}_sanitize_$t.log | head -1)"
+done
+echo "== 120 s WSPR drift check (BASELINE config 5, sampled channels, full length)"
+timeout 900 python tools/long_run_check.py > gpurun_out/${TAG}_long_run.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/${TAG}_long_run.log
 echo "== ncu launch list (same command as the bench line, fewer steps)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sdr_ -c 40 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu list rc=$?"
