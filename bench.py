@@ -295,6 +295,7 @@ def main():
     barrier()
     launches = b.launch_count - l0
     clocks = clk.stop()
+    role_profile = b.role_profile() if args.role_profile else None  # before the chunked e2e launches dilute the per-launch average
     total_ms = ev0[0].elapsed_time(ev0[-1])
     per_launch_ms = [ev0[k].elapsed_time(ev0[k + 1]) for k in range(args.steps)]
     cnt = gather_counters(float(nch) * ns * args.steps, total_ms, world, dev)
@@ -317,6 +318,30 @@ def main():
     e2e = dict(value=ecnt["samples"] / (ecnt["max_ms"] * 1e-3) / 1e6, unit=UNIT, h2d_bytes_per_step=int(2 * nch * ns * 2),
                d2h_bytes_per_step=int(nch * ns * 2), steps=args.e2e_steps, wire_format="int16 in / int16 out, pinned host memory",
                api="sdr_batch_process_host")
+
+    # ---- what the host link allows: the same planes copied both ways at once, nothing computed (bounds e2e from above)
+    try:
+        dI, dQ = torch.empty_like(I16), torch.empty_like(Q16)
+        dO = torch.zeros((nch, ns), dtype=torch.int16, device=dev)
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize()
+        best = None
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                dI.copy_(hI, non_blocking=True); dQ.copy_(hQ, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hO.copy_(dO, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        e2e["link_bound"] = dict(value=float(nch) * ns * world / best / 1e6, unit=UNIT, h2d_gbs=4.0 * nch * ns / best / 1e9,
+                                 note="both host planes up and one down concurrently with no kernel: the host-link ceiling of e2e per GPU x n_gpus")
+        e2e["link_frac"] = e2e["value"] / e2e["link_bound"]["value"]
+        del dI, dQ, dO
+    except Exception as e:
+        e2e["link_bound"] = dict(error=str(e))
 
     # ---- rooflines of the dominant kernel (sdr_pipeline_kernel: one launch per step)
     peaks, peak_src = measured_peaks()
@@ -363,7 +388,7 @@ def main():
                     data="synthetic",
                     config=config_dict(nch, nblk),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_fp32=fp32, cpu_baseline=cpu,
-                    role_profile=(b.role_profile() if args.role_profile else None), variant=args.variant or None,
+                    role_profile=role_profile, variant=args.variant or None,
                     diagnostic_workload=(None if cfg_id == CONFIG_ID else "BASELINE configs[%d], %d channels/GPU: NOT the headline metric" % (cfg_id - 1, nch)),
                     parity=parity, per_launch_ms=dict(mean=float(np.mean(per_launch_ms)), min=float(np.min(per_launch_ms)), max=float(np.max(per_launch_ms))))
         print(json.dumps(line), flush=True)
