@@ -17,6 +17,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-diag-suppress", "186"]
 
 
+AUX_LIB = os.path.join(HERE, "libsdr_aux.so")
+AUX_DEPS = ["sdr_aux.cu", "sdr_aux_core.cuh", "aux_tables.inc", os.path.join("..", "..", "include", "sdr_aux.h")]
+
+
 def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
@@ -49,6 +53,20 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def build_aux_library(force=False, verbose=False):
+    """Builds audiosdr_b200/libsdr_aux.so (pre-processor + I/Q generator, include/sdr_aux.h); returns its path."""
+    if not force and os.path.exists(AUX_LIB) and all(os.path.getmtime(os.path.join(CSRC, d)) <= os.path.getmtime(AUX_LIB) for d in AUX_DEPS):
+        return AUX_LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "sdr_aux.cu"), "-o", AUX_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return AUX_LIB
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_aux_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,484 @@
+/* sdr_aux.cu -- the two blocks either side of the receiver chain, batched: kernels and the C ABI
+ * of include/sdr_aux.h.  Per-lane arithmetic lives in sdr_aux_core.cuh (also run on the host by tests/emu/aux_emu.cpp).
+ *
+ *  I/Q generator (AudioIQgenerator.cpp:33-87): a 257-tap Hilbert FIR in its 64-product compact form plus a 128-sample delay,
+ *    purely feed-forward, so the kernel is parallel over channels AND time: one CTA = one channel x 4096 outputs, the
+ *    input span (+256 history) converted to float once into shared memory, one lane = 16 consecutive outputs with two
+ *    sliding 16-register windows.  192 unfused FP32 operations per output sample against 6 bytes of traffic: FP32-issue
+ *    bound.  History (the last 256 inputs per channel) is the only state, kept in two alternating buffers.
+ *  Pre-processor (AudioSDRpreProcessor.cpp:46-138): with the detector off a channel is a one-sample shift and/or a swap --
+ *    a feed-forward copy, 8 bytes moved per sample, HBM bound (pp_static_kernel).  Channels whose detector is running are
+ *    compacted into a list and handled block by block by pp_detect_kernel (lane = channel, 128-point FFT per block in
+ *    shared memory), because their correction may change from one block to the next.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdr_aux.h"
+#include "aux_tables.inc"
+#include "sdr_aux_core.cuh"
+
+__constant__ float c_iq_h[64];
+__constant__ float c_fft_tw[128];
+
+/* ================================================================== I/Q generator ==== */
+#define IQ_SEG 4096
+#define IQ_THREADS 256
+#define IQ_XS_WORDS (IQ_SEG + 256 + (IQ_SEG + 256) / 16 + 16)
+
+struct IqLaunch {
+  const int16_t *x; int16_t *oi, *oq;
+  unsigned long long in_pitch, out_pitch;
+  const int16_t *hist_in; int16_t *hist_out; /* [n_channels][256] */
+  const float2 *gains;                       /* (gainI, gainQ) per channel */
+  uint32_t n_samples, n_channels, segs;
+};
+
+__device__ __forceinline__ void iq_unpack8(const int4 v, float *f) {
+  const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    f[2 * i] = aux_q15_to_float((int)(int16_t)(w[i] & 0xFFFF));
+    f[2 * i + 1] = aux_q15_to_float(w[i] >> 16);
+  }
+}
+
+__global__ void __launch_bounds__(IQ_THREADS) iq_generate_kernel(const IqLaunch L) {
+  __shared__ float xs[IQ_XS_WORDS];
+  const uint32_t ch = blockIdx.x / L.segs, seg = blockIdx.x % L.segs;
+  const long base = (long)seg * IQ_SEG;
+  const int16_t *row = L.x + (size_t)ch * L.in_pitch;
+  /* the span [base-256, base+SEG) as floats at padded positions; 8 samples (16 bytes) per thread and pass */
+  for (int t = threadIdx.x; t < (IQ_SEG + 256) / 8; t += IQ_THREADS) {
+    const long n = base - 256 + 8 * t;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (n < 0) v = *reinterpret_cast<const int4 *>(L.hist_in + (size_t)ch * 256 + (256 + n));
+    else if (n < (long)L.n_samples) v = __ldg(reinterpret_cast<const int4 *>(row + n));
+    float f[8];
+    iq_unpack8(v, f);
+    float *dst = xs + 8 * t + ((8 * t) >> 4);
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[i] = f[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long n0 = base + 512 * warp + 16 * lane;
+  if (n0 >= (long)L.n_samples) return;
+  const int q0 = 256 + 512 * warp + 16 * lane;
+  float acc[16];
+  iq_lane_fir(xs, q0, c_iq_h, acc);
+  const float2 g = L.gains[ch];
+  uint32_t wi[8], wq[8];
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) {
+    const int i0 = aux_to_pcm(iq_lane_delayed(xs, q0, c), g.x), i1 = aux_to_pcm(iq_lane_delayed(xs, q0, c + 1), g.x);
+    const int q0v = aux_to_pcm(acc[c], g.y), q1v = aux_to_pcm(acc[c + 1], g.y);
+    wi[c >> 1] = ((uint32_t)i0 & 0xFFFFu) | ((uint32_t)i1 << 16);
+    wq[c >> 1] = ((uint32_t)q0v & 0xFFFFu) | ((uint32_t)q1v << 16);
+  }
+  uint4 *di = reinterpret_cast<uint4 *>(L.oi + (size_t)ch * L.out_pitch + n0);
+  uint4 *dq = reinterpret_cast<uint4 *>(L.oq + (size_t)ch * L.out_pitch + n0);
+  di[0] = make_uint4(wi[0], wi[1], wi[2], wi[3]); di[1] = make_uint4(wi[4], wi[5], wi[6], wi[7]);
+  dq[0] = make_uint4(wq[0], wq[1], wq[2], wq[3]); dq[1] = make_uint4(wq[4], wq[5], wq[6], wq[7]);
+}
+
+/* the last 256 inputs of every channel become the next call's history (other buffer: no ordering hazard) */
+__global__ void iq_history_kernel(const IqLaunch L) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t ch = idx >> 5, j = idx & 31;
+  if (ch >= L.n_channels) return;
+  const long n = (long)L.n_samples - 256 + 8 * (long)j;
+  int4 v;
+  if (n < 0) v = *reinterpret_cast<const int4 *>(L.hist_in + (size_t)ch * 256 + (256 + n));
+  else v = __ldg(reinterpret_cast<const int4 *>(L.x + (size_t)ch * L.in_pitch + n));
+  *reinterpret_cast<int4 *>(L.hist_out + (size_t)ch * 256 + 8 * j) = v;
+}
+
+/* ================================================================== pre-processor ==== */
+struct PpLaunch {
+  const int16_t *I, *Q; int16_t *oi, *oq;
+  unsigned long long in_pitch, out_pitch;
+  PpState *state;
+  uint32_t n_channels, n_blocks;
+  uint32_t *auto_list, *auto_count;
+};
+
+__global__ void pp_apply_kernel(PpState *st, uint32_t n_channels, const PpSetterCall *calls, uint32_t n_calls) {
+  const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= n_channels) return;
+  PpState s = st[ch];
+  for (uint32_t k = 0; k < n_calls; k++) {
+    const PpSetterCall c = calls[k];
+    if (c.channel == ch || c.channel == 0xFFFFFFFFu) pp_apply(s, c.setter, c.arg);
+  }
+  st[ch] = s;
+}
+
+__global__ void pp_list_kernel(const PpLaunch L) {
+  const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= L.n_channels) return;
+  if (L.state[ch].autod) L.auto_list[atomicAdd(L.auto_count, 1u)] = ch;
+}
+
+__device__ __forceinline__ void unpack_i16x8(const int4 v, int16_t *o) {
+  const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) { o[2 * i] = (int16_t)(w[i] & 0xFFFF); o[2 * i + 1] = (int16_t)(w[i] >> 16); }
+}
+__device__ __forceinline__ int4 pack_i16x8(const int16_t *o) {
+  int w[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) w[i] = (int)(((uint32_t)(uint16_t)o[2 * i]) | ((uint32_t)(uint16_t)o[2 * i + 1] << 16));
+  return make_int4(w[0], w[1], w[2], w[3]);
+}
+
+/* detector off: one thread = one 16-byte chunk of both rails.  8 bytes in + 8 bytes out per 2 samples... i.e. 8 B/sample. */
+__global__ void __launch_bounds__(256) pp_static_kernel(const PpLaunch L) {
+  const uint32_t chunks = L.n_blocks * 16; /* per channel */
+  const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t ch = (uint32_t)(idx / chunks), j = (uint32_t)(idx % chunks);
+  if (ch >= L.n_channels) return;
+  const PpState s = L.state[ch];
+  if (s.autod) return; /* pp_detect_kernel owns this channel for the call */
+  const int16_t *ri = L.I + (size_t)ch * L.in_pitch, *rq = L.Q + (size_t)ch * L.in_pitch;
+  const size_t n = (size_t)j * 8;
+  const int4 a = __ldg(reinterpret_cast<const int4 *>(ri + n)), b = __ldg(reinterpret_cast<const int4 *>(rq + n));
+  int4 oa = a, ob = b;
+  if (s.corr != 0) {
+    int16_t vi[8], vq[8], oi[8], oq[8];
+    unpack_i16x8(a, vi); unpack_i16x8(b, vq);
+    int16_t pi = (int16_t)s.saved, pq = (int16_t)s.saved;
+    if (j) { if (s.corr == 1) pi = ri[n - 1]; else pq = rq[n - 1]; }
+    pp_static_chunk(vi, vq, pi, pq, (j & 15) == 0, s.corr, 0, oi, oq);
+    oa = pack_i16x8(oi); ob = pack_i16x8(oq);
+  }
+  int4 *di = reinterpret_cast<int4 *>(L.oi + (size_t)ch * L.out_pitch + n), *dq = reinterpret_cast<int4 *>(L.oq + (size_t)ch * L.out_pitch + n);
+  *di = s.swap ? ob : oa;
+  *dq = s.swap ? oa : ob;
+}
+
+/* detector off: savedSample after the call = the delayed rail's last input sample (PP.cpp:62-65 / 67-70) */
+__global__ void pp_finish_kernel(const PpLaunch L) {
+  const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= L.n_channels) return;
+  const PpState s = L.state[ch];
+  if (s.autod || s.corr == 0) return;
+  const size_t last = (size_t)L.n_blocks * 128 - 1;
+  L.state[ch].saved = (s.corr == 1 ? L.I : L.Q)[(size_t)ch * L.in_pitch + last];
+}
+
+/* detector running: one warp = 32 listed channels, lane = channel, block after block.  Rows are staged through shared
+ * memory with whole-row (coalesced) transfers; a lane's row is 65 words apart from its neighbour's (odd: no conflicts). */
+#define PP_ROW_WORDS 65
+#define PP_DETECT_SMEM (256 * 32 * 4 + 2 * 32 * PP_ROW_WORDS * 4)
+__global__ void __launch_bounds__(32) pp_detect_kernel(const PpLaunch L) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  float *fft = reinterpret_cast<float *>(sm);
+  uint32_t *rowI = reinterpret_cast<uint32_t *>(sm + 256 * 32 * 4), *rowQ = rowI + 32 * PP_ROW_WORDS;
+  const int lane = threadIdx.x;
+  const uint32_t n_auto = *L.auto_count, first = blockIdx.x * 32;
+  if (first >= n_auto) return;
+  const int ch = first + lane < n_auto ? (int)L.auto_list[first + lane] : -1;
+  PpState s;
+  s.corr = s.saved = s.fail = s.succ = s.swap = s.autod = s.pad0 = s.pad1 = 0;
+  if (ch >= 0) s = L.state[ch];
+  for (uint32_t b = 0; b < L.n_blocks; b++) {
+    for (int r = 0; r < 32; r++) {
+      const int chr = __shfl_sync(0xFFFFFFFFu, ch, r);
+      if (chr >= 0) {
+        const uint32_t *si = reinterpret_cast<const uint32_t *>(L.I + (size_t)chr * L.in_pitch + (size_t)b * 128);
+        const uint32_t *sq = reinterpret_cast<const uint32_t *>(L.Q + (size_t)chr * L.in_pitch + (size_t)b * 128);
+        rowI[r * PP_ROW_WORDS + lane] = __ldg(si + lane); rowI[r * PP_ROW_WORDS + 32 + lane] = __ldg(si + 32 + lane);
+        rowQ[r * PP_ROW_WORDS + lane] = __ldg(sq + lane); rowQ[r * PP_ROW_WORDS + 32 + lane] = __ldg(sq + 32 + lane);
+      }
+    }
+    __syncwarp();
+    int16_t *ri = reinterpret_cast<int16_t *>(rowI + lane * PP_ROW_WORDS), *rq = reinterpret_cast<int16_t *>(rowQ + lane * PP_ROW_WORDS);
+    if (ch >= 0) {
+      pp_correct_block(ri, rq, s);
+      if (s.autod) {
+        float *mine = fft + lane;
+        for (int i = 0; i < 128; i++) {
+          mine[(2 * i) * 32] = aux_q15_to_float(ri[i]);
+          mine[(2 * i + 1) * 32] = aux_q15_to_float(rq[i]);
+        }
+        pp_fft128(mine, 32, c_fft_tw);
+        pp_detect(mine, 32, s);
+      }
+    }
+    __syncwarp();
+    for (int r = 0; r < 32; r++) {
+      const int chr = __shfl_sync(0xFFFFFFFFu, ch, r), sw = __shfl_sync(0xFFFFFFFFu, s.swap, r);
+      if (chr >= 0) {
+        const uint32_t *a = (sw ? rowQ : rowI) + r * PP_ROW_WORDS, *c = (sw ? rowI : rowQ) + r * PP_ROW_WORDS;
+        uint32_t *di = reinterpret_cast<uint32_t *>(L.oi + (size_t)chr * L.out_pitch + (size_t)b * 128);
+        uint32_t *dq = reinterpret_cast<uint32_t *>(L.oq + (size_t)chr * L.out_pitch + (size_t)b * 128);
+        di[lane] = a[lane]; di[32 + lane] = a[32 + lane];
+        dq[lane] = c[lane]; dq[32 + lane] = c[32 + lane];
+      }
+    }
+    __syncwarp();
+  }
+  if (ch >= 0) L.state[ch] = s;
+}
+
+/* ================================================================== host side ==== */
+static thread_local std::string g_err;
+static int fail(int code, const std::string &m) { g_err = m; return code; }
+#define CK(call)                                                                                                    \
+  do {                                                                                                              \
+    cudaError_t e_ = (call);                                                                                        \
+    if (e_ != cudaSuccess) return fail(SDR_AUX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+static int upload_tables() {
+  float h[64], tw[128];
+  memcpy(h, AUX_IQ_HILBERT, sizeof h);
+  memcpy(tw, AUX_FFT_TW, sizeof tw);
+  CK(cudaMemcpyToSymbol(c_iq_h, h, sizeof h));
+  CK(cudaMemcpyToSymbol(c_fft_tw, tw, sizeof tw));
+  return 0;
+}
+
+static int check_planes(const void *a, const void *b, const void *c, const void *d, size_t in_pitch, size_t out_pitch, uint32_t n_blocks) {
+  if (!a || !c || !d || n_blocks == 0) return fail(SDR_AUX_EINVAL, "null plane or n_blocks == 0");
+  if ((in_pitch & 7) || (out_pitch & 7) || in_pitch < (size_t)n_blocks * 128 || out_pitch < (size_t)n_blocks * 128)
+    return fail(SDR_AUX_EINVAL, "pitch must be a multiple of 8 elements and >= 128*n_blocks");
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) return fail(SDR_AUX_EINVAL, "planes must be 16-byte aligned");
+  if (c == a || c == b || d == a || d == b || c == d) return fail(SDR_AUX_EINVAL, "output planes must not alias the inputs or each other");
+  return 0;
+}
+
+/* device staging for the *_process_host entry points */
+struct Staging {
+  int16_t *p[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t pitch = 0; uint32_t blocks = 0;
+  int ensure(uint32_t n_channels, uint32_t n_blocks, int planes) {
+    if (n_blocks <= blocks && p[planes - 1]) return 0;
+    release();
+    pitch = (size_t)n_blocks * 128;
+    for (int i = 0; i < planes; i++)
+      if (cudaMalloc(&p[i], pitch * n_channels * sizeof(int16_t)) != cudaSuccess) { release(); return fail(SDR_AUX_ENOMEM, "cudaMalloc(staging) failed"); }
+    blocks = n_blocks;
+    return 0;
+  }
+  void release() { for (auto &q : p) { if (q) cudaFree(q); q = nullptr; } blocks = 0; }
+};
+
+/* ------------------------------------------------------------------ pre-processor ---- */
+struct sdr_preproc {
+  uint32_t n = 0; int device = 0;
+  PpState *state = nullptr;
+  uint32_t *list = nullptr, *count = nullptr;
+  PpSetterCall *d_calls = nullptr; size_t d_calls_cap = 0;
+  std::vector<PpSetterCall> pending;
+  bool auto_possible = false; /* some channel may have its detector on */
+  uint64_t launches = 0;
+  Staging stg;
+};
+
+extern "C" int sdr_preproc_create(sdr_preproc_t **out, uint32_t n_channels, int device) {
+  if (!out || n_channels == 0) return fail(SDR_AUX_EINVAL, "sdr_preproc_create: bad arguments");
+  CK(cudaSetDevice(device));
+  if (int rc = upload_tables()) return rc;
+  CK(cudaFuncSetAttribute(pp_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_DETECT_SMEM));
+  sdr_preproc *h = new sdr_preproc();
+  h->n = n_channels; h->device = device;
+  if (cudaMalloc(&h->state, sizeof(PpState) * n_channels) != cudaSuccess || cudaMalloc(&h->list, 4 * (size_t)n_channels) != cudaSuccess ||
+      cudaMalloc(&h->count, 4) != cudaSuccess) { sdr_preproc_destroy(h); return fail(SDR_AUX_ENOMEM, "cudaMalloc failed"); }
+  CK(cudaMemset(h->state, 0, sizeof(PpState) * n_channels)); /* PP.h:63-72 initialisers: everything 0 / false */
+  *out = h;
+  return 0;
+}
+
+extern "C" void sdr_preproc_destroy(sdr_preproc_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->state); cudaFree(h->list); cudaFree(h->count); cudaFree(h->d_calls);
+  h->stg.release();
+  delete h;
+}
+
+extern "C" int sdr_preproc_set(sdr_preproc_t *h, const uint32_t *channels, uint32_t n, uint32_t setter, int32_t arg) {
+  if (!h) return fail(SDR_AUX_EINVAL, "null handle");
+  if (setter < 1 || setter > 4) return fail(SDR_AUX_EINVAL, "unknown pre-processor setter " + std::to_string(setter));
+  if (setter == SDR_PP_setI2SerrorCompensation && (arg < -1 || arg > 1)) return fail(SDR_AUX_EINVAL, "I2S compensation must be -1, 0 or +1");
+  if (setter == SDR_PP_startAutoI2SerrorDetection) h->auto_possible = true;
+  if (!channels) { h->pending.push_back({0xFFFFFFFFu, setter, arg, 0}); return 0; }
+  for (uint32_t i = 0; i < n; i++) if (channels[i] >= h->n) return fail(SDR_AUX_EINVAL, "channel out of range");
+  for (uint32_t i = 0; i < n; i++) h->pending.push_back({channels[i], setter, arg, 0});
+  return 0;
+}
+
+static int pp_flush(sdr_preproc *h, cudaStream_t st) {
+  if (h->pending.empty()) return 0;
+  if (h->pending.size() > h->d_calls_cap) {
+    cudaFree(h->d_calls); h->d_calls = nullptr;
+    h->d_calls_cap = h->pending.size() * 2 + 64;
+    if (cudaMalloc(&h->d_calls, sizeof(PpSetterCall) * h->d_calls_cap) != cudaSuccess) { h->d_calls_cap = 0; return fail(SDR_AUX_ENOMEM, "cudaMalloc(calls) failed"); }
+  }
+  /* pageable source: the copy is staged before the call returns, so the vector may be cleared right away */
+  CK(cudaMemcpyAsync(h->d_calls, h->pending.data(), sizeof(PpSetterCall) * h->pending.size(), cudaMemcpyHostToDevice, st));
+  pp_apply_kernel<<<(h->n + 255) / 256, 256, 0, st>>>(h->state, h->n, h->d_calls, (uint32_t)h->pending.size());
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st)); /* d_calls may be reallocated by the next flush */
+  h->pending.clear();
+  h->launches++;
+  return 0;
+}
+
+extern "C" int sdr_preproc_get_status(sdr_preproc_t *h, const uint32_t *channels, uint32_t n, sdr_preproc_status *out) {
+  if (!h || !out) return fail(SDR_AUX_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  if (int rc = pp_flush(h, 0)) return rc;
+  CK(cudaDeviceSynchronize());
+  const uint32_t cnt = channels ? n : h->n;
+  for (uint32_t i = 0; i < cnt; i++) {
+    const uint32_t c = channels ? channels[i] : i;
+    if (c >= h->n) return fail(SDR_AUX_EINVAL, "channel out of range");
+    PpState s;
+    CK(cudaMemcpy(&s, h->state + c, sizeof s, cudaMemcpyDeviceToHost));
+    out[i].auto_detect = s.autod; out[i].correction = s.corr; out[i].failure_count = s.fail;
+    out[i].success_count = s.succ; out[i].saved_sample = s.saved; out[i].swap = s.swap;
+  }
+  return 0;
+}
+
+extern "C" int sdr_preproc_process_device(sdr_preproc_t *h, const int16_t *I, const int16_t *Q, size_t in_pitch, int16_t *I_out,
+                                          int16_t *Q_out, size_t out_pitch, uint32_t n_blocks, void *cuda_stream) {
+  if (!h) return fail(SDR_AUX_EINVAL, "null handle");
+  if (!Q) return fail(SDR_AUX_EINVAL, "null plane");
+  if (int rc = check_planes(I, Q, I_out, Q_out, in_pitch, out_pitch, n_blocks)) return rc;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (int rc = pp_flush(h, st)) return rc;
+  PpLaunch L = {I, Q, I_out, Q_out, in_pitch, out_pitch, h->state, h->n, n_blocks, h->list, h->count};
+  const uint32_t tb = (h->n + 255) / 256;
+  if (h->auto_possible) {
+    CK(cudaMemsetAsync(h->count, 0, 4, st));
+    pp_list_kernel<<<tb, 256, 0, st>>>(L);
+    h->launches++;
+  }
+  const unsigned long long threads = (unsigned long long)h->n * n_blocks * 16;
+  pp_static_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(L);
+  pp_finish_kernel<<<tb, 256, 0, st>>>(L);
+  h->launches += 2;
+  if (h->auto_possible) {
+    pp_detect_kernel<<<(h->n + 31) / 32, 32, PP_DETECT_SMEM, st>>>(L);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sdr_preproc_process_host(sdr_preproc_t *h, const int16_t *I, const int16_t *Q, size_t in_pitch, int16_t *I_out,
+                                        int16_t *Q_out, size_t out_pitch, uint32_t n_blocks) {
+  if (!h || !I || !Q || !I_out || !Q_out || n_blocks == 0) return fail(SDR_AUX_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->device));
+  if (int rc = h->stg.ensure(h->n, n_blocks, 4)) return rc;
+  const size_t w = (size_t)n_blocks * 128 * 2, dp = h->stg.pitch * 2;
+  CK(cudaMemcpy2DAsync(h->stg.p[0], dp, I, in_pitch * 2, w, h->n, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpy2DAsync(h->stg.p[1], dp, Q, in_pitch * 2, w, h->n, cudaMemcpyHostToDevice, 0));
+  if (int rc = sdr_preproc_process_device(h, h->stg.p[0], h->stg.p[1], h->stg.pitch, h->stg.p[2], h->stg.p[3], h->stg.pitch, n_blocks, nullptr)) return rc;
+  CK(cudaMemcpy2DAsync(I_out, out_pitch * 2, h->stg.p[2], dp, w, h->n, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpy2DAsync(Q_out, out_pitch * 2, h->stg.p[3], dp, w, h->n, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+extern "C" uint64_t sdr_preproc_launch_count(const sdr_preproc_t *h) { return h ? h->launches : 0; }
+
+/* ------------------------------------------------------------------ I/Q generator ---- */
+struct sdr_iqgen {
+  uint32_t n = 0; int device = 0;
+  int16_t *hist[2] = {nullptr, nullptr};
+  int cur = 0;
+  float2 *gains = nullptr;
+  std::vector<float2> h_gains;
+  bool gains_dirty = true;
+  uint64_t launches = 0;
+  Staging stg;
+};
+
+extern "C" int sdr_iqgen_create(sdr_iqgen_t **out, uint32_t n_channels, int device) {
+  if (!out || n_channels == 0) return fail(SDR_AUX_EINVAL, "sdr_iqgen_create: bad arguments");
+  CK(cudaSetDevice(device));
+  if (int rc = upload_tables()) return rc;
+  sdr_iqgen *h = new sdr_iqgen();
+  h->n = n_channels; h->device = device;
+  h->h_gains.assign(n_channels, make_float2(1.0f, 1.0f)); /* IQ.h:72-73 */
+  if (cudaMalloc(&h->hist[0], 512 * (size_t)n_channels) != cudaSuccess || cudaMalloc(&h->hist[1], 512 * (size_t)n_channels) != cudaSuccess ||
+      cudaMalloc(&h->gains, sizeof(float2) * n_channels) != cudaSuccess) { sdr_iqgen_destroy(h); return fail(SDR_AUX_ENOMEM, "cudaMalloc failed"); }
+  CK(cudaMemset(h->hist[0], 0, 512 * (size_t)n_channels)); /* the static buffers start at zero, IQ.cpp:37-38 */
+  CK(cudaMemset(h->hist[1], 0, 512 * (size_t)n_channels));
+  *out = h;
+  return 0;
+}
+
+extern "C" void sdr_iqgen_destroy(sdr_iqgen_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->hist[0]); cudaFree(h->hist[1]); cudaFree(h->gains);
+  h->stg.release();
+  delete h;
+}
+
+extern "C" int sdr_iqgen_set_gain_balance(sdr_iqgen_t *h, const uint32_t *channels, uint32_t n, float balance) {
+  if (!h) return fail(SDR_AUX_EINVAL, "null handle");
+  const float2 g = make_float2(balance, (float)(1.0 / (double)balance)); /* IQ.h:58-59 */
+  if (!channels) { for (auto &x : h->h_gains) x = g; }
+  else {
+    for (uint32_t i = 0; i < n; i++) if (channels[i] >= h->n) return fail(SDR_AUX_EINVAL, "channel out of range");
+    for (uint32_t i = 0; i < n; i++) h->h_gains[channels[i]] = g;
+  }
+  h->gains_dirty = true;
+  return 0;
+}
+
+extern "C" int sdr_iqgen_process_device(sdr_iqgen_t *h, const int16_t *X, size_t in_pitch, int16_t *I_out, int16_t *Q_out,
+                                        size_t out_pitch, uint32_t n_blocks, void *cuda_stream) {
+  if (!h) return fail(SDR_AUX_EINVAL, "null handle");
+  if (int rc = check_planes(X, nullptr, I_out, Q_out, in_pitch, out_pitch, n_blocks)) return rc;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (h->gains_dirty) {
+    CK(cudaMemcpyAsync(h->gains, h->h_gains.data(), sizeof(float2) * h->n, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st)); /* pageable source may change after we return */
+    h->gains_dirty = false;
+  }
+  IqLaunch L;
+  L.x = X; L.oi = I_out; L.oq = Q_out; L.in_pitch = in_pitch; L.out_pitch = out_pitch;
+  L.hist_in = h->hist[h->cur]; L.hist_out = h->hist[h->cur ^ 1]; L.gains = h->gains;
+  L.n_samples = n_blocks * 128; L.n_channels = h->n; L.segs = (L.n_samples + IQ_SEG - 1) / IQ_SEG;
+  const unsigned long long grid = (unsigned long long)h->n * L.segs;
+  if (grid > 0x7FFFFFFFull) return fail(SDR_AUX_EINVAL, "too many channel-segments for one launch");
+  iq_generate_kernel<<<(unsigned)grid, IQ_THREADS, 0, st>>>(L);
+  iq_history_kernel<<<(h->n * 32 + 255) / 256, 256, 0, st>>>(L);
+  CK(cudaGetLastError());
+  h->cur ^= 1;
+  h->launches += 2;
+  return 0;
+}
+
+extern "C" int sdr_iqgen_process_host(sdr_iqgen_t *h, const int16_t *X, size_t in_pitch, int16_t *I_out, int16_t *Q_out,
+                                      size_t out_pitch, uint32_t n_blocks) {
+  if (!h || !X || !I_out || !Q_out || n_blocks == 0) return fail(SDR_AUX_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->device));
+  if (int rc = h->stg.ensure(h->n, n_blocks, 3)) return rc;
+  const size_t w = (size_t)n_blocks * 128 * 2, dp = h->stg.pitch * 2;
+  CK(cudaMemcpy2DAsync(h->stg.p[0], dp, X, in_pitch * 2, w, h->n, cudaMemcpyHostToDevice, 0));
+  if (int rc = sdr_iqgen_process_device(h, h->stg.p[0], h->stg.pitch, h->stg.p[1], h->stg.p[2], h->stg.pitch, n_blocks, nullptr)) return rc;
+  CK(cudaMemcpy2DAsync(I_out, out_pitch * 2, h->stg.p[1], dp, w, h->n, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpy2DAsync(Q_out, out_pitch * 2, h->stg.p[2], dp, w, h->n, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+extern "C" uint64_t sdr_iqgen_launch_count(const sdr_iqgen_t *h) { return h ? h->launches : 0; }
+
+extern "C" const char *sdr_aux_last_error(void) { return g_err.c_str(); }
+extern "C" const char *sdr_aux_version(void) { return "audiosdr_b200 aux 0.1 (sm_100a)"; }

@@ -36,7 +36,8 @@ class AudioStream {
     return b;
   }
   audio_block_t *receiveReadOnly(unsigned int index = 0) { return receiveWritable(index); }
-  static audio_block_t *allocate(void) { return 0; }
+  /* AudioSDR never allocates; AudioIQgenerator allocates its Q output block every update (AudioIQgenerator.cpp:47) */
+  static audio_block_t *allocate(void) { static audio_block_t pool[4]; static unsigned k = 0; return &pool[k++ & 3]; }
   void transmit(audio_block_t *block, unsigned char index = 0) { if (index < 4) sent[index] = block; }
   static void release(audio_block_t *) {}
   unsigned char num_inputs;

@@ -51,4 +51,17 @@ static inline void arm_biquad_cascade_df1_f32(const arm_biquad_casd_df1_inst_f32
     pIn = pDst;
   }
 }
+
+/* --- FFT entry points used by AudioSDRpreProcessor.cpp:88-89.  CMSIS-DSP itself is not in the reference tree; the
+ *     transform is the restatement in oracle/aux_fft128.h (see its header: rounding unpinned, decisions checked). */
+#include "../aux_fft128.h"
+typedef struct { uint16_t fftLen; } arm_cfft_instance_f32;
+static const arm_cfft_instance_f32 arm_cfft_sR_f32_len128 = {128};
+static inline void arm_cfft_f32(const arm_cfft_instance_f32 *S, float32_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag) {
+  (void)ifftFlag; (void)bitReverseFlag; /* the reference calls (.., 0, 1): forward, natural-order output */
+  if (S->fftLen == 128) aux_cfft128_forward(p1);
+}
+static inline void arm_cmplx_mag_squared_f32(float32_t *pSrc, float32_t *pDst, uint32_t numSamples) {
+  aux_cmplx_mag_squared(pSrc, pDst, numSamples);
+}
 #endif
