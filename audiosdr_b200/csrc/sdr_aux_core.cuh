@@ -128,7 +128,7 @@ AUX_HD void pp_correct_block(int16_t *I, int16_t *Q, PpState &s) {
   }
 }
 
-/* 128-point forward FFT, radix-2 decimation in frequency, the operation network of oracle/aux_fft128.h evaluated in
+/* 128-point forward FFT, radix-2 decimation in frequency, the fixed operation network documented in DESIGN.md (section 11), evaluated in
  * place WITHOUT the final reordering: element e (buf[(2e)*stride], buf[(2e+1)*stride]) ends up holding X[brev7(e)].
  * tw = (cos, -sin)(2 pi k/128). */
 AUX_HD void pp_fft128(float *buf, int stride, const float *tw) {

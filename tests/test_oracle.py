@@ -16,7 +16,7 @@ import harness
 import signals as S
 from oracle import ref_client as rc
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("aux_"))
 
 
 def load_golden(path):
