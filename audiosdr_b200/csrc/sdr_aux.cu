@@ -171,23 +171,29 @@ __global__ void pp_finish_kernel(const PpLaunch L) {
   L.state[ch].saved = (s.corr == 1 ? L.I : L.Q)[(size_t)ch * L.in_pitch + last];
 }
 
-/* detector running: one warp = 32 listed channels, lane = channel, block after block.  Rows are staged through shared
- * memory with whole-row (coalesced) transfers; a lane's row is 65 words apart from its neighbour's (odd: no conflicts). */
+/* detector running: one CTA = 32 listed channels (lane = channel) x PP_W warps that share each channel's work, block
+ * after block.  Rows are staged through shared memory with whole-row (coalesced) transfers; a lane's row is 65 words from
+ * its neighbour's (odd: no bank conflicts); the FFT buffer is [256][32] floats, lane-interleaved.  Warp 0 owns the
+ * per-channel state (correction, counters); the butterflies of a stage, the conversions and the rows are split over
+ * the warps with a CTA barrier between dependent phases. */
+#define PP_W 8
 #define PP_ROW_WORDS 65
-#define PP_DETECT_SMEM (256 * 32 * 4 + 2 * 32 * PP_ROW_WORDS * 4)
-__global__ void __launch_bounds__(32) pp_detect_kernel(const PpLaunch L) {
+#define PP_DETECT_SMEM (256 * 32 * 4 + 2 * 32 * PP_ROW_WORDS * 4 + 2 * 32 * 4)
+__global__ void __launch_bounds__(32 * PP_W) pp_detect_kernel(const PpLaunch L) {
   extern __shared__ __align__(16) unsigned char sm[];
   float *fft = reinterpret_cast<float *>(sm);
   uint32_t *rowI = reinterpret_cast<uint32_t *>(sm + 256 * 32 * 4), *rowQ = rowI + 32 * PP_ROW_WORDS;
-  const int lane = threadIdx.x;
+  int *sh_det = reinterpret_cast<int *>(rowQ + 32 * PP_ROW_WORDS), *sh_swap = sh_det + 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t n_auto = *L.auto_count, first = blockIdx.x * 32;
   if (first >= n_auto) return;
   const int ch = first + lane < n_auto ? (int)L.auto_list[first + lane] : -1;
   PpState s;
   s.corr = s.saved = s.fail = s.succ = s.swap = s.autod = s.pad0 = s.pad1 = 0;
-  if (ch >= 0) s = L.state[ch];
+  if (ch >= 0) s = L.state[ch]; /* every warp reads it; only warp 0's copy evolves and is written back */
+  float *mine = fft + lane;
   for (uint32_t b = 0; b < L.n_blocks; b++) {
-    for (int r = 0; r < 32; r++) {
+    for (int r = w; r < 32; r += PP_W) {
       const int chr = __shfl_sync(0xFFFFFFFFu, ch, r);
       if (chr >= 0) {
         const uint32_t *si = reinterpret_cast<const uint32_t *>(L.I + (size_t)chr * L.in_pitch + (size_t)b * 128);
@@ -196,23 +202,42 @@ __global__ void __launch_bounds__(32) pp_detect_kernel(const PpLaunch L) {
         rowQ[r * PP_ROW_WORDS + lane] = __ldg(sq + lane); rowQ[r * PP_ROW_WORDS + 32 + lane] = __ldg(sq + 32 + lane);
       }
     }
-    __syncwarp();
+    __syncthreads();
     int16_t *ri = reinterpret_cast<int16_t *>(rowI + lane * PP_ROW_WORDS), *rq = reinterpret_cast<int16_t *>(rowQ + lane * PP_ROW_WORDS);
-    if (ch >= 0) {
-      pp_correct_block(ri, rq, s);
-      if (s.autod) {
-        float *mine = fft + lane;
-        for (int i = 0; i < 128; i++) {
+    if (w == 0) {
+      if (ch >= 0) pp_correct_block(ri, rq, s);
+      sh_det[lane] = ch >= 0 && s.autod;
+      sh_swap[lane] = s.swap;
+    }
+    __syncthreads();
+    const bool det = sh_det[lane] != 0;
+    if (__any_sync(0xFFFFFFFFu, det)) { /* same lanes, same flags in every warp: uniform over the CTA */
+      if (det) {
+        for (int i = w; i < 128; i += PP_W) {
           mine[(2 * i) * 32] = aux_q15_to_float(ri[i]);
           mine[(2 * i + 1) * 32] = aux_q15_to_float(rq[i]);
         }
-        pp_fft128(mine, 32, c_fft_tw);
-        pp_detect(mine, 32, s);
       }
+      __syncthreads();
+      for (int st = 0; st < 7; st++) {
+        if (det) pp_fft128_stage(mine, 32, c_fft_tw, st, w, PP_W);
+        __syncthreads();
+      }
+      float pw[128 / PP_W];
+      if (det) {
+#pragma unroll
+        for (int k = 0; k < 128 / PP_W; k++) pw[k] = pp_power(mine, 32, w + k * PP_W);
+      }
+      __syncthreads();
+      if (det) {
+#pragma unroll
+        for (int k = 0; k < 128 / PP_W; k++) mine[(w + k * PP_W) * 32] = pw[k];
+      }
+      __syncthreads();
+      if (w == 0 && det) pp_decide(mine, 32, s);
     }
-    __syncwarp();
-    for (int r = 0; r < 32; r++) {
-      const int chr = __shfl_sync(0xFFFFFFFFu, ch, r), sw = __shfl_sync(0xFFFFFFFFu, s.swap, r);
+    for (int r = w; r < 32; r += PP_W) {
+      const int chr = __shfl_sync(0xFFFFFFFFu, ch, r), sw = sh_swap[r];
       if (chr >= 0) {
         const uint32_t *a = (sw ? rowQ : rowI) + r * PP_ROW_WORDS, *c = (sw ? rowI : rowQ) + r * PP_ROW_WORDS;
         uint32_t *di = reinterpret_cast<uint32_t *>(L.oi + (size_t)chr * L.out_pitch + (size_t)b * 128);
@@ -221,9 +246,9 @@ __global__ void __launch_bounds__(32) pp_detect_kernel(const PpLaunch L) {
         dq[lane] = c[lane]; dq[32 + lane] = c[32 + lane];
       }
     }
-    __syncwarp();
+    __syncthreads();
   }
-  if (ch >= 0) L.state[ch] = s;
+  if (w == 0 && ch >= 0) L.state[ch] = s;
 }
 
 /* ================================================================== host side ==== */
@@ -368,7 +393,7 @@ extern "C" int sdr_preproc_process_device(sdr_preproc_t *h, const int16_t *I, co
   pp_finish_kernel<<<tb, 256, 0, st>>>(L);
   h->launches += 2;
   if (h->auto_possible) {
-    pp_detect_kernel<<<(h->n + 31) / 32, 32, PP_DETECT_SMEM, st>>>(L);
+    pp_detect_kernel<<<(h->n + 31) / 32, 32 * PP_W, PP_DETECT_SMEM, st>>>(L);
     h->launches++;
   }
   CK(cudaGetLastError());

@@ -131,42 +131,47 @@ AUX_HD void pp_correct_block(int16_t *I, int16_t *Q, PpState &s) {
 /* 128-point forward FFT, radix-2 decimation in frequency, the fixed operation network documented in DESIGN.md (section 11), evaluated in
  * place WITHOUT the final reordering: element e (buf[(2e)*stride], buf[(2e+1)*stride]) ends up holding X[brev7(e)].
  * tw = (cos, -sin)(2 pi k/128). */
-AUX_HD void pp_fft128(float *buf, int stride, const float *tw) {
-  for (int s = 0; s < 7; s++) {
-    const int half = 64 >> s;
-    AUX_UNROLLN(4) for (int t = 0; t < 64; t++) {
-      const int j = t & (half - 1);
-      const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
-      float *a = buf + (2 * i0) * stride, *b = buf + (2 * i1) * stride;
-      const float ar = a[0], ai = a[stride], br = b[0], bi = b[stride];
-      const float wr = tw[2 * (j << s)], wi = tw[2 * (j << s) + 1];
-      const float tr = ar - br, ti = ai - bi;
-      a[0] = ar + br;
-      a[stride] = ai + bi;
-      const float p0 = tr * wr, p1 = ti * wi, p2 = tr * wi, p3 = ti * wr;
-      b[0] = p0 - p1;
-      b[stride] = p2 + p3;
-    }
+/* one stage s (0..6) of the network, butterflies t = t0, t0 + tstep, ... < 64 (the kernel splits t over its warps) */
+AUX_HD void pp_fft128_stage(float *buf, int stride, const float *tw, int s, int t0, int tstep) {
+  const int half = 64 >> s;
+  AUX_UNROLLN(4) for (int t = t0; t < 64; t += tstep) {
+    const int j = t & (half - 1);
+    const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
+    float *a = buf + (2 * i0) * stride, *b = buf + (2 * i1) * stride;
+    const float ar = a[0], ai = a[stride], br = b[0], bi = b[stride];
+    const float wr = tw[2 * (j << s)], wi = tw[2 * (j << s) + 1];
+    const float tr = ar - br, ti = ai - bi;
+    a[0] = ar + br;
+    a[stride] = ai + bi;
+    const float p0 = tr * wr, p1 = ti * wi, p2 = tr * wi, p3 = ti * wr;
+    b[0] = p0 - p1;
+    b[stride] = p2 + p3;
   }
+}
+AUX_HD void pp_fft128(float *buf, int stride, const float *tw) {
+  for (int s = 0; s < 7; s++) pp_fft128_stage(buf, stride, tw, s, 0, 1);
 }
 
 /* Power spectrum, scan and the detector's state machine, PP.cpp:89-118.  buf as left by pp_fft128. */
-AUX_HD void pp_detect(float *buf, int stride, PpState &s) {
-  for (int e = 0; e < 128; e++) { /* arm_cmplx_mag_squared_f32 in place: slot e is read (as 2e, 2e+1 >= e) before it is written */
-    const float re = buf[(2 * e) * stride], im = buf[(2 * e + 1) * stride];
-    const float p = re * re, q = im * im;
-    buf[e * stride] = p + q;
-  }
+/* |element e|^2 = re^2 + im^2, two products and one sum (arm_cmplx_mag_squared_f32, PP.cpp:89) */
+AUX_HD float pp_power(const float *buf, int stride, int e) {
+  const float re = buf[(2 * e) * stride], im = buf[(2 * e + 1) * stride];
+  const float p = re * re, q = im * im;
+  return p + q;
+}
+
+/* Scan and the detector's state machine, PP.cpp:91-118.  pw[e*stride] = power of element e (bin brev7(e)). */
+AUX_HD void pp_decide(const float *pw, int stride, PpState &s) {
   float average_power = 0.0f, maximum_power = 0.0f;
   int maxLine = 0;
   for (int i = 5; i < 123; i++) {
-    const float v = buf[aux_brev7(i) * stride];
+    const float v = pw[aux_brev7(i) * stride];
     average_power = average_power + v;
     if (v > maximum_power) { maxLine = i; maximum_power = v; }
   }
   average_power = average_power / 118.0f;
   if ((double)maximum_power > 10.0 * (double)average_power) { /* the product is exact in double: an exact compare */
-    const float imbalance_ratio = maximum_power / buf[aux_brev7(128 - maxLine) * stride]; /* maxLine >= 5 here */
+    const float imbalance_ratio = maximum_power / pw[aux_brev7(128 - maxLine) * stride]; /* maxLine >= 5 here */
     if (imbalance_ratio < 10.0f) s.fail++;
     else s.fail = 0;
     if (s.fail > 10) {
@@ -178,6 +183,12 @@ AUX_HD void pp_detect(float *buf, int stride, PpState &s) {
     s.succ++;
   }
   if (s.succ > 1000) s.autod = 0;
+}
+
+/* Power spectrum in place (slot e is read, as 2e and 2e+1 >= e, before it is written) + decisions: the one-thread form */
+AUX_HD void pp_detect(float *buf, int stride, PpState &s) {
+  for (int e = 0; e < 128; e++) buf[e * stride] = pp_power(buf, stride, e);
+  pp_decide(buf, stride, s);
 }
 
 /* ------------------------------------------------------------------ I/Q generator ---- */
