@@ -73,12 +73,22 @@ __global__ void __launch_bounds__(IQ_THREADS) iq_generate_kernel(const IqLaunch 
   iq_lane_fir(xs, q0, c_iq_h, acc);
   const float2 g = L.gains[ch];
   uint32_t wi[8], wq[8];
+  if (g.x == 1.0f && g.y == 1.0f) { /* the constructor's balance (IQ.h:72-73): uniform over the CTA, no FP64, no range test */
 #pragma unroll
-  for (int c = 0; c < 16; c += 2) {
-    const int i0 = aux_to_pcm(iq_lane_delayed(xs, q0, c), g.x), i1 = aux_to_pcm(iq_lane_delayed(xs, q0, c + 1), g.x);
-    const int q0v = aux_to_pcm(acc[c], g.y), q1v = aux_to_pcm(acc[c + 1], g.y);
-    wi[c >> 1] = ((uint32_t)i0 & 0xFFFFu) | ((uint32_t)i1 << 16);
-    wq[c >> 1] = ((uint32_t)q0v & 0xFFFFu) | ((uint32_t)q1v << 16);
+    for (int c = 0; c < 16; c += 2) {
+      const int i0 = aux_to_pcm_unit(iq_lane_delayed(xs, q0, c)), i1 = aux_to_pcm_unit(iq_lane_delayed(xs, q0, c + 1));
+      const int q0v = aux_to_pcm_unit(acc[c]), q1v = aux_to_pcm_unit(acc[c + 1]);
+      wi[c >> 1] = ((uint32_t)i0 & 0xFFFFu) | ((uint32_t)i1 << 16);
+      wq[c >> 1] = ((uint32_t)q0v & 0xFFFFu) | ((uint32_t)q1v << 16);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+      const int i0 = aux_to_pcm(iq_lane_delayed(xs, q0, c), g.x), i1 = aux_to_pcm(iq_lane_delayed(xs, q0, c + 1), g.x);
+      const int q0v = aux_to_pcm(acc[c], g.y), q1v = aux_to_pcm(acc[c + 1], g.y);
+      wi[c >> 1] = ((uint32_t)i0 & 0xFFFFu) | ((uint32_t)i1 << 16);
+      wq[c >> 1] = ((uint32_t)q0v & 0xFFFFu) | ((uint32_t)q1v << 16);
+    }
   }
   uint4 *di = reinterpret_cast<uint4 *>(L.oi + (size_t)ch * L.out_pitch + n0);
   uint4 *dq = reinterpret_cast<uint4 *>(L.oq + (size_t)ch * L.out_pitch + n0);

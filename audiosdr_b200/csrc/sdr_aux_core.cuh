@@ -57,6 +57,16 @@ AUX_HD int aux_to_pcm(float v, float gain) {
   return (int)(int16_t)i;
 }
 
+/* the gain == 1 case of aux_to_pcm for |v| < 256, branch-free (the I/Q generator's outputs never exceed 2 * sum|h| < 5) */
+AUX_HD int aux_to_pcm_unit(float v) {
+  const float a = fabsf(v);
+  const float hi = a * 32767.0f;
+  const float err = fmaf(a, 32767.0f, -hi);
+  int r = (int)hi;
+  r -= ((float)r == hi && err < 0.0f) ? 1 : 0;
+  return v < 0.0f ? -r : r;
+}
+
 AUX_HD int aux_brev7(int i) {
 #if defined(__CUDA_ARCH__)
   return (int)(__brev((unsigned)i) >> 25);

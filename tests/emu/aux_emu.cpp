@@ -39,7 +39,7 @@ static long check_pcm() {
   long bad = 0, n = 0;
   const float gains[] = {1.0f, 1.1f, 1.0f / 1.1f, 0.5f, 3.0f, 70000.0f, -1.0f};
   for (int q = -32768; q <= 32767; q++)
-    for (float g : gains) { const float v = aux_q15_to_float(q); n++; if (aux_to_pcm(v, g) != ref_pcm(v, g)) bad++; }
+    for (float g : gains) { const float v = aux_q15_to_float(q); n++; if (aux_to_pcm(v, g) != ref_pcm(v, g)) bad++; if (g == 1.0f && (int16_t)aux_to_pcm_unit(v) != ref_pcm(v, g)) bad++; }
   for (long i = 0; i < 20000000; i++) { /* random floats over the Hilbert output range and beyond */
     uint32_t bits = rnd() ^ (rnd() << 16);
     float v; memcpy(&v, &bits, 4);
@@ -47,6 +47,13 @@ static long check_pcm() {
     const float g = (i & 3) ? 1.0f : gains[(i >> 2) % 7];
     n++;
     if (aux_to_pcm(v, g) != ref_pcm(v, g)) bad++;
+    if (fabsf(v) < 256.0f && (int16_t)aux_to_pcm_unit(v) != ref_pcm(v, 1.0f)) bad++;
+  }
+  { /* the unit-gain path skips the range test: the generator's outputs are bounded by 2 * sum|h| * (32768/32767) */
+    double sum = 0;
+    for (int k = 0; k < 64; k++) sum += fabs((double)tabf(AUX_IQ_HILBERT, k));
+    if (2.0 * sum * 1.0001 >= 256.0) bad++;
+    printf("sum|h| = %.4f (bound on |Q| = %.4f)\n", sum, 2.0 * sum * 1.0001);
   }
   printf("to_pcm: %ld values, mismatches %ld\n", n, bad);
   return bad;
