@@ -251,3 +251,15 @@ def test_aux_error_behaviour(aux):
     g.process(a, c, d)
     torch.cuda.synchronize()
     assert int(c.abs().max()) == 0 and int(d.abs().max()) == 0
+
+
+def test_cpp_host_classes_run_on_the_gpu(aux, tmp_path):
+    """include/SdrBatch.hpp and include/SdrAux.hpp driven from C++ on the device (the CPU tier only proves they link)."""
+    import subprocess
+    from audiosdr_b200 import build
+    for src, lib, tag in (("host_class_smoke.cpp", build.build_library(), "sdr_batch"), ("aux_class_smoke.cpp", build.build_aux_library(), "sdr_aux")):
+        exe = str(tmp_path / src.replace(".cpp", ""))
+        subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", src), "-o", exe, "-L" + os.path.dirname(lib), "-l" + tag,
+                        "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and "GPU_OK" in r.stdout and "NO_DEVICE" not in r.stdout, r.stdout + r.stderr
