@@ -11,7 +11,7 @@ from .api import (AGC_FAST, AGC_MEDIUM, AGC_OFF, AGC_SLOW, AM, AUDIO_2100, AUDIO
                   AUDIO_2900, AUDIO_3100, AUDIO_3300, AUDIO_AM, AUDIO_BYPASS, AUDIO_CW, AUDIO_WSPR, CW_LSB, CW_USB,
                   FMT_F32, FMT_I16, LSB, SAM, SETTERS, USB, WSPR, ChannelStatus, SdrBatch, SdrError, lib_path,
                   load_library)
-from .aux import AuxError, IQGeneratorBatch, PreProcessorBatch
+from .aux import AuxError, GrabberBatch, IQGeneratorBatch, PreProcessorBatch
 from .build import build_aux_library, build_library
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,8 +1,9 @@
 """audiosdr_b200/aux.py -- Python mirrors of the two blocks either side of the receiver chain, over the C ABI of
 include/sdr_aux.h (audiosdr_b200/libsdr_aux.so; CUDA only, no CPU fallback):
 
-  PreProcessorBatch  <-  class AudioSDRpreProcessor  (AudioSDRpreProcessor.h:49-73): same method names, channel selector first
-  IQGeneratorBatch   <-  class AudioIQgenerator      (AudioIQgenerator.h:49-107)
+  PreProcessorBatch  <-  class AudioSDRpreProcessor    (AudioSDRpreProcessor.h:49-73): same method names, channel selector first
+  IQGeneratorBatch   <-  class AudioIQgenerator        (AudioIQgenerator.h:49-107)
+  GrabberBatch       <-  class AudioGrabberComplex256  (AudioGrabberComplex256.h:46-64)
 
 Channel selector: None = every channel, an int, or a sequence of ints.  Planes are int16 [n_channels, >= 128*n_blocks]."""
 import ctypes as C
@@ -16,7 +17,8 @@ PP_SETTERS = dict(startAutoI2SerrorDetection=1, stopAutoI2SerrorDetection=2, set
 EXPORTS = ["sdr_preproc_create", "sdr_preproc_destroy", "sdr_preproc_set", "sdr_preproc_get_status", "sdr_preproc_process_device",
            "sdr_preproc_process_host", "sdr_preproc_launch_count", "sdr_iqgen_create", "sdr_iqgen_destroy",
            "sdr_iqgen_set_gain_balance", "sdr_iqgen_process_device", "sdr_iqgen_process_host", "sdr_iqgen_launch_count",
-           "sdr_aux_last_error", "sdr_aux_version"]
+           "sdr_grabber_create", "sdr_grabber_destroy", "sdr_grabber_process_device", "sdr_grabber_new_data_available",
+           "sdr_grabber_grab", "sdr_grabber_grab_device", "sdr_aux_last_error", "sdr_aux_version"]
 
 
 class AuxError(RuntimeError):
@@ -58,6 +60,12 @@ def load_library(path=None):
     L.sdr_iqgen_process_device.argtypes = [vp, vp, sz, vp, vp, sz, u32, vp]
     L.sdr_iqgen_process_host.argtypes = [vp, vp, sz, vp, vp, sz, u32]
     L.sdr_iqgen_launch_count.argtypes = [vp]; L.sdr_iqgen_launch_count.restype = C.c_uint64
+    L.sdr_grabber_create.argtypes = [C.POINTER(vp), u32, C.c_int]
+    L.sdr_grabber_destroy.argtypes = [vp]; L.sdr_grabber_destroy.restype = None
+    L.sdr_grabber_process_device.argtypes = [vp, vp, vp, sz, u32, vp]
+    L.sdr_grabber_new_data_available.argtypes = [vp, u32]
+    L.sdr_grabber_grab.argtypes = [vp, vp, u32, vp]
+    L.sdr_grabber_grab_device.argtypes = [vp, vp, vp]
     L.sdr_aux_last_error.restype = C.c_char_p
     L.sdr_aux_version.restype = C.c_char_p
     if path is None:
@@ -187,3 +195,44 @@ class IQGeneratorBatch(_Base):
     @property
     def launch_count(self):
         return int(self.L.sdr_iqgen_launch_count(self.h))
+
+
+class GrabberBatch(_Base):
+    """AudioGrabberComplex256 for n_channels: process() = update() x n_blocks, grab() = the last complete 256-sample snapshot."""
+
+    def __init__(self, n_channels, device=0, _lib=None):
+        self.L = _lib or load_library()
+        self.n_channels = int(n_channels)
+        self.h = C.c_void_p()
+        self._check(self.L.sdr_grabber_create(C.byref(self.h), self.n_channels, int(device)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sdr_grabber_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def process(self, I, Q, n_blocks=None, stream=None):
+        n_blocks = int(n_blocks if n_blocks is not None else I.shape[1] // N_BLOCK)
+        _check_dev(self.n_channels, I, Q)
+        assert I.stride(0) == Q.stride(0)
+        sp = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        self._check(self.L.sdr_grabber_process_device(self.h, I.data_ptr(), Q.data_ptr(), I.stride(0), n_blocks, sp))
+
+    def newDataAvailable(self, channel):
+        r = self.L.sdr_grabber_new_data_available(self.h, int(channel))
+        if r < 0:
+            self._check(r)
+        return bool(r)
+
+    def grab(self, channels=None):
+        """int16 [n, 512] (re, im interleaved) or None while no pair of blocks has completed (the reference's grab() then
+        leaves the destination untouched)."""
+        p, n, keep = _sel(channels)
+        cnt = n if channels is not None else self.n_channels
+        out = np.empty((cnt, 512), np.int16)
+        r = self.L.sdr_grabber_grab(self.h, p, n, out.ctypes.data)
+        if r < 0:
+            self._check(r)
+        return out if r > 0 else None

@@ -13,6 +13,7 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -259,6 +260,50 @@ __global__ void __launch_bounds__(32 * PP_W) pp_detect_kernel(const PpLaunch L) 
     __syncthreads();
   }
   if (w == 0 && ch >= 0) L.state[ch] = s;
+}
+
+/* ================================================================== grabber ==== */
+/* AudioGrabberComplex256.cpp:50-72 over a whole call: the snapshot after the call is the last pair of blocks that completed
+ * (global block index odd), its first half possibly carried over from the previous call.  96 threads per channel: 64 write
+ * the snapshot (4 complex samples each), 32 the carried half. */
+struct GrabLaunch {
+  const int16_t *I, *Q; unsigned long long pitch;
+  const int16_t *half_in; int16_t *half_out; /* [n_channels][256]: first block of an incomplete pair, interleaved */
+  int16_t *outb;                             /* [n_channels][512] */
+  uint32_t n_channels, n_blocks, t0_odd;
+};
+
+__device__ __forceinline__ int4 grab_interleave4(const int16_t *I, const int16_t *Q) { /* 4 samples of each rail -> re,im,re,im,... */
+  const uint2 a = *reinterpret_cast<const uint2 *>(I), b = *reinterpret_cast<const uint2 *>(Q);
+  int4 o;
+  o.x = (int)__byte_perm(a.x, b.x, 0x5410); o.y = (int)__byte_perm(a.x, b.x, 0x7632);
+  o.z = (int)__byte_perm(a.y, b.y, 0x5410); o.w = (int)__byte_perm(a.y, b.y, 0x7632);
+  return o;
+}
+
+__global__ void grab_update_kernel(const GrabLaunch L) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t ch = idx / 96, j = idx % 96;
+  if (ch >= L.n_channels) return;
+  const int n = (int)L.n_blocks;
+  const int16_t *ri = L.I + (size_t)ch * L.pitch, *rq = L.Q + (size_t)ch * L.pitch;
+  if (j < 64) {
+    /* last block of the call that completes a pair */
+    int bs = ((int)L.t0_odd + n - 1) & 1 ? n - 1 : n - 2;
+    if (bs < 0) return; /* no pair completed in this call: the snapshot stays */
+    const int second = j >= 32, s4 = (int)(j & 31) * 4; /* which block of the pair, first sample of the chunk */
+    int4 v;
+    if (second) v = grab_interleave4(ri + (size_t)bs * 128 + s4, rq + (size_t)bs * 128 + s4);
+    else if (bs >= 1) v = grab_interleave4(ri + (size_t)(bs - 1) * 128 + s4, rq + (size_t)(bs - 1) * 128 + s4);
+    else v = *reinterpret_cast<const int4 *>(L.half_in + (size_t)ch * 256 + 2 * s4);
+    *reinterpret_cast<int4 *>(L.outb + (size_t)ch * 512 + 8 * j) = v;
+  } else {
+    const int s4 = (int)(j - 64) * 4;
+    int4 v;
+    if (((int)L.t0_odd + n) & 1) v = grab_interleave4(ri + (size_t)(n - 1) * 128 + s4, rq + (size_t)(n - 1) * 128 + s4);
+    else v = *reinterpret_cast<const int4 *>(L.half_in + (size_t)ch * 256 + 2 * s4); /* not observable; keeps the buffers in step */
+    *reinterpret_cast<int4 *>(L.half_out + (size_t)ch * 256 + 2 * s4) = v;
+  }
 }
 
 /* ================================================================== host side ==== */
@@ -514,6 +559,81 @@ extern "C" int sdr_iqgen_process_host(sdr_iqgen_t *h, const int16_t *X, size_t i
 }
 
 extern "C" uint64_t sdr_iqgen_launch_count(const sdr_iqgen_t *h) { return h ? h->launches : 0; }
+
+/* ------------------------------------------------------------------ grabber ---- */
+struct sdr_grabber {
+  uint32_t n = 0; int device = 0;
+  int16_t *half[2] = {nullptr, nullptr}, *outb = nullptr;
+  int cur = 0;
+  uint64_t blocks = 0;     /* update() calls so far (every channel advances together) */
+  bool valid = false;      /* _dataBufferValid */
+  std::vector<uint8_t> fresh; /* _newDataIsAvailable per channel */
+};
+
+extern "C" int sdr_grabber_create(sdr_grabber_t **out, uint32_t n_channels, int device) {
+  if (!out || n_channels == 0) return fail(SDR_AUX_EINVAL, "sdr_grabber_create: bad arguments");
+  CK(cudaSetDevice(device));
+  sdr_grabber *h = new sdr_grabber();
+  h->n = n_channels; h->device = device; h->fresh.assign(n_channels, 0);
+  if (cudaMalloc(&h->half[0], 512 * (size_t)n_channels) != cudaSuccess || cudaMalloc(&h->half[1], 512 * (size_t)n_channels) != cudaSuccess ||
+      cudaMalloc(&h->outb, 1024 * (size_t)n_channels) != cudaSuccess) { sdr_grabber_destroy(h); return fail(SDR_AUX_ENOMEM, "cudaMalloc failed"); }
+  CK(cudaMemset(h->half[0], 0, 512 * (size_t)n_channels));
+  CK(cudaMemset(h->half[1], 0, 512 * (size_t)n_channels));
+  CK(cudaMemset(h->outb, 0, 1024 * (size_t)n_channels));
+  *out = h;
+  return 0;
+}
+
+extern "C" void sdr_grabber_destroy(sdr_grabber_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->half[0]); cudaFree(h->half[1]); cudaFree(h->outb);
+  delete h;
+}
+
+extern "C" int sdr_grabber_process_device(sdr_grabber_t *h, const int16_t *I, const int16_t *Q, size_t pitch, uint32_t n_blocks, void *cuda_stream) {
+  if (!h || !I || !Q || n_blocks == 0) return fail(SDR_AUX_EINVAL, "bad arguments");
+  if ((pitch & 7) || pitch < (size_t)n_blocks * 128 || (((uintptr_t)I | (uintptr_t)Q) & 15)) return fail(SDR_AUX_EINVAL, "planes must be 16-byte aligned, pitch a multiple of 8 and >= 128*n_blocks");
+  CK(cudaSetDevice(h->device));
+  GrabLaunch L = {I, Q, pitch, h->half[h->cur], h->half[h->cur ^ 1], h->outb, h->n, n_blocks, (uint32_t)(h->blocks & 1)};
+  const unsigned long long threads = (unsigned long long)h->n * 96;
+  grab_update_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(L);
+  CK(cudaGetLastError());
+  const bool completed = ((h->blocks & 1) + n_blocks) >= 2; /* some block of this call had an odd global index */
+  h->cur ^= 1;
+  h->blocks += n_blocks;
+  if (completed) { h->valid = true; std::fill(h->fresh.begin(), h->fresh.end(), (uint8_t)1); }
+  return 0;
+}
+
+extern "C" int sdr_grabber_new_data_available(sdr_grabber_t *h, uint32_t channel) {
+  if (!h || channel >= h->n) return fail(SDR_AUX_EINVAL, "bad arguments");
+  return h->fresh[channel];
+}
+
+extern "C" int sdr_grabber_grab(sdr_grabber_t *h, const uint32_t *channels, uint32_t n, int16_t *dest) {
+  if (!h || !dest) return fail(SDR_AUX_EINVAL, "bad arguments");
+  const uint32_t cnt = channels ? n : h->n;
+  for (uint32_t i = 0; i < cnt; i++) if ((channels ? channels[i] : i) >= h->n) return fail(SDR_AUX_EINVAL, "channel out of range");
+  CK(cudaSetDevice(h->device));
+  int written = 0;
+  if (h->valid) { /* AudioGrabberComplex256.cpp:83-88 */
+    CK(cudaDeviceSynchronize());
+    if (!channels) { CK(cudaMemcpy(dest, h->outb, 1024 * (size_t)h->n, cudaMemcpyDeviceToHost)); }
+    else for (uint32_t i = 0; i < cnt; i++) CK(cudaMemcpy(dest + (size_t)i * 512, h->outb + (size_t)channels[i] * 512, 1024, cudaMemcpyDeviceToHost));
+    written = (int)cnt;
+  }
+  for (uint32_t i = 0; i < cnt; i++) h->fresh[channels ? channels[i] : i] = 0; /* AudioGrabberComplex256.cpp:90 */
+  return written;
+}
+
+extern "C" int sdr_grabber_grab_device(sdr_grabber_t *h, int16_t *dest, void *cuda_stream) {
+  if (!h || !dest) return fail(SDR_AUX_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->device));
+  if (h->valid) CK(cudaMemcpyAsync(dest, h->outb, 1024 * (size_t)h->n, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+  std::fill(h->fresh.begin(), h->fresh.end(), (uint8_t)0);
+  return h->valid ? 1 : 0;
+}
 
 extern "C" const char *sdr_aux_last_error(void) { return g_err.c_str(); }
 extern "C" const char *sdr_aux_version(void) { return "audiosdr_b200 aux 0.1 (sm_100a)"; }

@@ -2,6 +2,7 @@
  *
  *   sdr::PreProcessorBatch  <-  class AudioSDRpreProcessor  (AudioSDRpreProcessor.h:49-73)
  *   sdr::IQGeneratorBatch   <-  class AudioIQgenerator      (AudioIQgenerator.h:49-107)
+ *   sdr::GrabberBatch       <-  class AudioGrabberComplex256 (AudioGrabberComplex256.h:46-64)
  *
  * Every public method of the reference keeps its name and argument meaning with a channel selector in front
  * (sdr::Channels from SdrBatch.hpp: one id, a vector of ids, or sdr::all); update() becomes process() over int16 planes.
@@ -75,6 +76,28 @@ class IQGeneratorBatch {
     if (rc != SDR_AUX_OK) throw std::runtime_error(std::string(what) + ": " + sdr_aux_last_error());
   }
   sdr_iqgen_t *h_;
+};
+
+/* AudioGrabberComplex256 (AudioGrabberComplex256.h:46-64) for n channels */
+class GrabberBatch {
+ public:
+  explicit GrabberBatch(uint32_t n_channels, int device = 0) : h_(nullptr) { check(sdr_grabber_create(&h_, n_channels, device), "sdr_grabber_create"); }
+  ~GrabberBatch() { sdr_grabber_destroy(h_); }
+  GrabberBatch(const GrabberBatch &) = delete;
+  GrabberBatch &operator=(const GrabberBatch &) = delete;
+  /* update() for every channel, n_blocks blocks each; device planes */
+  void process(const int16_t *I, const int16_t *Q, size_t pitch, uint32_t n_blocks, void *cuda_stream = nullptr) {
+    check(sdr_grabber_process_device(h_, I, Q, pitch, n_blocks, cuda_stream), "sdr_grabber_process_device");
+  }
+  bool newDataAvailable(uint32_t c) { const int r = sdr_grabber_new_data_available(h_, c); if (r < 0) check(r, "sdr_grabber_new_data_available"); return r != 0; }
+  /* grab(destination) of one channel: 512 int16 to host memory; false (destination untouched) before the first complete pair */
+  bool grab(uint32_t c, int16_t *destination) { const int r = sdr_grabber_grab(h_, &c, 1, destination); if (r < 0) check(r, "sdr_grabber_grab"); return r > 0; }
+
+ private:
+  static void check(int rc, const char *what) {
+    if (rc != SDR_AUX_OK) throw std::runtime_error(std::string(what) + ": " + sdr_aux_last_error());
+  }
+  sdr_grabber_t *h_;
 };
 
 }  // namespace sdr

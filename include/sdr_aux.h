@@ -3,6 +3,7 @@
  *
  *   sdr_preproc_*   replaces  class AudioSDRpreProcessor   AudioSDRpreProcessor.h:49-73, update() AudioSDRpreProcessor.cpp:46-138
  *   sdr_iqgen_*     replaces  class AudioIQgenerator       AudioIQgenerator.h:49-107,   update() AudioIQgenerator.cpp:33-87
+ *   sdr_grabber_*   replaces  class AudioGrabberComplex256 AudioGrabberComplex256.h:46-64, update()/grab() AudioGrabberComplex256.cpp:50-91
  *
  * Planes are int16 (the reference's audio_block_t wire format), channel-major: sample s of channel c is plane[c*pitch + s],
  * pitch in elements.  Base pointers must be 16-byte aligned and pitches multiples of 8.  Output planes must not overlap the
@@ -66,6 +67,25 @@ int sdr_iqgen_process_device(sdr_iqgen_t *h, const int16_t *X, size_t in_pitch, 
 int sdr_iqgen_process_host(sdr_iqgen_t *h, const int16_t *X, size_t in_pitch, int16_t *I_out, int16_t *Q_out,
                            size_t out_pitch, uint32_t n_blocks);
 uint64_t sdr_iqgen_launch_count(const sdr_iqgen_t *h);
+
+/* ---------------------------------------------------------------- complex snapshot grabber ---- */
+/* replaces class AudioGrabberComplex256 (AudioGrabberComplex256.h:46-64): every update() appends one block of interleaved
+ * (re, im) samples to a two-block buffer; each time the buffer fills, it becomes the snapshot grab() hands out
+ * (AudioGrabberComplex256.cpp:50-91).  No arithmetic: the batched form is a gather of the last complete pair of blocks. */
+typedef struct sdr_grabber sdr_grabber_t;
+
+int sdr_grabber_create(sdr_grabber_t **out, uint32_t n_channels, int device);
+void sdr_grabber_destroy(sdr_grabber_t *h);
+/* AudioGrabberComplex256::update() for every channel, n_blocks times; device planes as for the pre-processor */
+int sdr_grabber_process_device(sdr_grabber_t *h, const int16_t *I, const int16_t *Q, size_t pitch, uint32_t n_blocks, void *cuda_stream);
+/* newDataAvailable() of one channel: 1 / 0, negative on error */
+int sdr_grabber_new_data_available(sdr_grabber_t *h, uint32_t channel);
+/* grab() for the listed channels (NULL: all): 512 int16 per channel = 256 complex samples, to HOST memory
+ * dest[i*512 .. i*512+511].  Before the first complete pair nothing is written (the reference's _dataBufferValid), and the
+ * call still clears the channels' new-data flags.  Returns the number of channels written, negative on error. */
+int sdr_grabber_grab(sdr_grabber_t *h, const uint32_t *channels, uint32_t n, int16_t *dest);
+/* all channels, device to device: dest[n_channels][512]; returns 0 when nothing was valid yet, 1 when written */
+int sdr_grabber_grab_device(sdr_grabber_t *h, int16_t *dest, void *cuda_stream);
 
 const char *sdr_aux_last_error(void);
 const char *sdr_aux_version(void);

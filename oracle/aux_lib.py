@@ -14,9 +14,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 N_BLOCK = 128
-KIND = {"pp": 1, "iq": 2}
+KIND = {"pp": 1, "iq": 2, "grab": 3}
 OPS = {"pp": {"startAutoI2SerrorDetection": 1, "stopAutoI2SerrorDetection": 2, "setI2SerrorCompensation": 3, "swapIQ": 4},
-       "iq": {"setGainBalance": 1}}
+       "iq": {"setGainBalance": 1}, "grab": {}}
 PP_STATUS = ("auto_detect", "correction", "failure_count", "success_count", "saved_sample", "swap")
 _lib = None
 
@@ -32,6 +32,8 @@ def lib():
         _lib.ora_aux_run.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int]
         _lib.ora_aux_power128.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.ora_grab_run.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.ora_grab_run.restype = None
     return _lib
 
 
@@ -60,6 +62,22 @@ def run(kind, planes, events=(), threads=4):
     return o0, o1, st
 
 
+def grab_run(I, Q):
+    """AudioGrabberComplex256: n_blocks updates from a fresh object, then grab().  Returns (out int32 [C, 512] with -1 where
+    grab() delivers nothing, flags int32 [C, 2] = {newDataAvailable before the grab, buffer valid})."""
+    I = np.ascontiguousarray(I, np.int16); Q = np.ascontiguousarray(Q, np.int16)
+    nch, ns = I.shape
+    out = np.empty((nch, 512), np.int32); flags = np.empty((nch, 2), np.int32)
+    lib().ora_grab_run(nch, ns // N_BLOCK, I.ctypes.data, Q.ctypes.data, out.ctypes.data, flags.ctypes.data)
+    return out, flags
+
+
+def ref_grab_run(I, Q, jobs=8):
+    """The same from the unmodified reference (oracle/_ref/refaux kind 3)."""
+    _, _, st = ref_run("grab", (I, Q), (), jobs=jobs)
+    return st[:, 8:520].copy(), st[:, :2].copy()
+
+
 def power128(I, Q):
     p = np.empty(128, np.float32)
     I = np.ascontiguousarray(I, np.int16); Q = np.ascontiguousarray(Q, np.int16)
@@ -83,7 +101,7 @@ def _write_request(path, kind, planes, events):
         f.write(b"REFAUX01" + struct.pack("<IIII", KIND[kind], nch, ns // N_BLOCK, nev))
         f.write(blob)
         f.write(a.tobytes())
-        if kind == "pp":
+        if kind in ("pp", "grab"):
             f.write(np.ascontiguousarray(planes[1], np.int16).tobytes())
     return nch, ns
 

@@ -3,6 +3,7 @@
  * Host harness around the UNMODIFIED neighbour blocks of the receiver chain
  *   /root/reference/SRC/AudioSDRlib/AudioSDRpreProcessor.{h,cpp}   kind 1
  *   /root/reference/SRC/AudioSDRlib/AudioIQgenerator.{h,cpp}       kind 2
+ *   /root/reference/SRC/AudioSDRlib/AudioGrabberComplex256.{h,cpp} kind 3 (row 3: no arithmetic, a 256-sample snapshot)
  * #included by path (never copied) through oracle/shim/.  Built by oracle/Makefile into oracle/_ref/refaux.
  * The pre-processor's FFT comes from oracle/aux_fft128.h (CMSIS-DSP is not in the reference tree).
  * One fork()ed child per channel: AudioIQgenerator keeps its history in function statics (AudioIQgenerator.cpp:37-40).
@@ -18,6 +19,9 @@
  * Opcodes : kind 1: 1 startAutoI2SerrorDetection, 2 stopAutoI2SerrorDetection, 3 setI2SerrorCompensation(a0), 4 swapIQ(a0)
  *           kind 2: 1 setGainBalance(a0)
  * Status  : kind 1: {autoDetect, I2Scorrection, failureCount, successCount, savedSample, IQswap}
+ *           kind 3: n_status = 520: {newDataAvailable() before the grab, _dataBufferValid, 0.., then at [8..519] the 512 int16
+ *                   that grab() delivered after the last block (-1 where grab() left the destination untouched)}; inputs as
+ *                   kind 1, no output planes (out0/out1 are written as zeros)
  */
 #include <algorithm>
 #include <chrono>
@@ -37,11 +41,13 @@
 #include "SRC/AudioSDRlib/AudioSDRpreProcessor.cpp"
 #include "SRC/AudioSDRlib/AudioIQgenerator.h"
 #include "SRC/AudioSDRlib/AudioIQgenerator.cpp"
+#include "SRC/AudioSDRlib/AudioGrabberComplex256.h"
+#include "SRC/AudioSDRlib/AudioGrabberComplex256.cpp"
 #undef private
 
 struct Event { uint32_t channel, block, opcode; float a0; };
 struct Header { char magic[8]; uint32_t kind, n_channels, n_blocks, n_extra; };
-static const int N_STATUS = 8;
+static const int N_STATUS = 8, N_STATUS_GRAB = 520;
 
 struct Request {
   Header h;
@@ -57,7 +63,7 @@ static bool load(const char *path, Request &r) {
   if (fread(map, 1, len, f) != (size_t)len) { fclose(f); return false; }
   fclose(f);
   memcpy(&r.h, map, sizeof(Header));
-  if (memcmp(r.h.magic, "REFAUX01", 8) || (r.h.kind != 1 && r.h.kind != 2)) { fprintf(stderr, "bad request\n"); return false; }
+  if (memcmp(r.h.magic, "REFAUX01", 8) || r.h.kind < 1 || r.h.kind > 3) { fprintf(stderr, "bad request\n"); return false; }
   const char *p = map + sizeof(Header);
   r.events.resize(r.h.n_extra);
   memcpy(r.events.data(), p, sizeof(Event) * r.h.n_extra);
@@ -65,7 +71,7 @@ static bool load(const char *path, Request &r) {
   size_t ns = (size_t)r.h.n_blocks * 128;
   r.p0 = (const int16_t *)p;
   r.p1 = r.p0 + (size_t)r.h.n_channels * ns;
-  size_t need = sizeof(Header) + sizeof(Event) * r.h.n_extra + 2 * (r.h.kind == 1 ? 2 : 1) * (size_t)r.h.n_channels * ns;
+  size_t need = sizeof(Header) + sizeof(Event) * r.h.n_extra + 2 * (r.h.kind != 2 ? 2 : 1) * (size_t)r.h.n_channels * ns;
   if ((size_t)len < need) { fprintf(stderr, "request truncated\n"); return false; }
   return true;
 }
@@ -109,7 +115,27 @@ static void run_channel(const Request &r, uint32_t ch, int16_t *o0, int16_t *o1,
   std::vector<Event> ev = events_for(r, ch);
   size_t ei = 0, ns = (size_t)r.h.n_blocks * 128;
   static audio_block_t ba, bb;
-  memset(status, 0, sizeof(int32_t) * N_STATUS);
+  memset(status, 0, sizeof(int32_t) * (r.h.kind == 3 ? N_STATUS_GRAB : N_STATUS));
+  if (r.h.kind == 3) {
+    AudioGrabberComplex256 *g = make_zeroed<AudioGrabberComplex256>();
+    const int16_t *I = r.p0 + ch * ns, *Q = r.p1 + ch * ns;
+    for (uint32_t b = 0; b < r.h.n_blocks; b++) {
+      memcpy(ba.data, I + (size_t)b * 128, 256);
+      memcpy(bb.data, Q + (size_t)b * 128, 256);
+      g->oracle_feed(0, &ba); g->oracle_feed(1, &bb);
+      g->update();
+    }
+    memset(o0, 0, ns * 2); memset(o1, 0, ns * 2);
+    status[0] = g->newDataAvailable() ? 1 : 0;
+    status[1] = g->_dataBufferValid ? 1 : 0;
+    int16_t dest[512];
+    int16_t untouched[512];
+    memset(dest, 0x55, sizeof dest); memset(untouched, 0x55, sizeof untouched);
+    g->grab(dest);
+    for (int i = 0; i < 512; i++) status[8 + i] = (status[1] || dest[i] != untouched[i]) ? dest[i] : -1;
+    status[2] = g->newDataAvailable() ? 1 : 0;
+    return;
+  }
   if (r.h.kind == 1) {
     AudioSDRpreProcessor *pp = make_zeroed<AudioSDRpreProcessor>();
     const int16_t *I = r.p0 + ch * ns, *Q = r.p1 + ch * ns;
@@ -149,11 +175,12 @@ static int cmd_run(const char *req, const char *resp, int jobs) {
   Request r;
   if (!load(req, r)) return 2;
   size_t ns = (size_t)r.h.n_blocks * 128, nch = r.h.n_channels;
-  size_t out_len = sizeof(Header) + nch * ns * 4 + nch * N_STATUS * 4;
+  const int nst = r.h.kind == 3 ? N_STATUS_GRAB : N_STATUS;
+  size_t out_len = sizeof(Header) + nch * ns * 4 + nch * nst * 4;
   char *out = (char *)mmap(0, out_len, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
   if (out == MAP_FAILED) { perror("mmap"); return 2; }
   Header oh; memcpy(oh.magic, "REFAUO01", 8);
-  oh.kind = r.h.kind; oh.n_channels = r.h.n_channels; oh.n_blocks = r.h.n_blocks; oh.n_extra = N_STATUS;
+  oh.kind = r.h.kind; oh.n_channels = r.h.n_channels; oh.n_blocks = r.h.n_blocks; oh.n_extra = nst;
   memcpy(out, &oh, sizeof(oh));
   int16_t *o0 = (int16_t *)(out + sizeof(Header)), *o1 = o0 + nch * ns;
   int32_t *status = (int32_t *)(out + sizeof(Header) + nch * ns * 4);
@@ -162,7 +189,7 @@ static int cmd_run(const char *req, const char *resp, int jobs) {
     while (running >= jobs) { int st; wait(&st); running--; if (!WIFEXITED(st) || WEXITSTATUS(st)) failed++; }
     pid_t pid = fork();
     if (pid < 0) { perror("fork"); return 2; }
-    if (pid == 0) { run_channel(r, ch, o0 + ch * ns, o1 + ch * ns, status + ch * N_STATUS); _exit(0); }
+    if (pid == 0) { run_channel(r, ch, o0 + ch * ns, o1 + ch * ns, status + ch * nst); _exit(0); }
     running++;
   }
   while (running > 0) { int st; wait(&st); running--; if (!WIFEXITED(st) || WEXITSTATUS(st)) failed++; }

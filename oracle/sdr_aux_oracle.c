@@ -192,6 +192,33 @@ int ora_aux_run(int kind, uint32_t n_channels, uint32_t n_blocks, const void *ev
   return 0;
 }
 
+/* ------------------------------------------------------------------ grabber ----
+ * AudioGrabberComplex256::update() / grab(), AudioGrabberComplex256.cpp:50-91 ("GR"): no arithmetic.  Runs n_blocks updates
+ * from a fresh object per channel, then one grab(): out[c][512] = the interleaved (re, im) samples of the last COMPLETE pair
+ * of blocks (untouched = -1 in every slot when no pair has completed yet), flags[c] = {newDataAvailable() before the grab,
+ * _dataBufferValid}. */
+void ora_grab_run(uint32_t n_channels, uint32_t n_blocks, const int16_t *I, const int16_t *Q, int32_t *out, int32_t *flags) {
+  const size_t ns = (size_t)n_blocks * NB;
+  for (uint32_t c = 0; c < n_channels; c++) {
+    int16_t buffer[512], outBuffer[512];
+    uint16_t buffStart = 0;
+    int valid = 0, fresh = 0;
+    memset(buffer, 0, sizeof buffer); memset(outBuffer, 0, sizeof outBuffer);
+    for (uint32_t b = 0; b < n_blocks; b++) { /* GR.cpp:58-69 (_transferringData is false outside grab()) */
+      const int16_t *re = I + c * ns + (size_t)b * NB, *im = Q + c * ns + (size_t)b * NB;
+      int16_t *dst = buffer + buffStart;
+      for (int i = 0; i < NB; i++) { *dst++ = re[i]; *dst++ = im[i]; } /* GR.cpp:39-47 */
+      buffStart = (uint16_t)((buffStart + 256) % 512);
+      if (buffStart == 0) {
+        for (int i = 0; i < 512; i++) outBuffer[i] = buffer[i];
+        fresh = 1; valid = 1;
+      }
+    }
+    flags[2 * c] = fresh; flags[2 * c + 1] = valid;
+    for (int i = 0; i < 512; i++) out[(size_t)c * 512 + i] = valid ? outBuffer[i] : -1; /* GR.cpp:83-88 */
+  }
+}
+
 /* natural-order power spectrum of one block as the detector sees it (for the float64-DFT decision test) */
 void ora_aux_power128(const int16_t *I, const int16_t *Q, float *power) {
   float buf[256];

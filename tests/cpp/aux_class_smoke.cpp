@@ -23,6 +23,9 @@ int main() {
     g.process_host(X.data(), 256, gi.data(), gq.data(), 256, 2);
     /* the impulse comes out of the I rail 128 samples later (within 1 LSB), x 1.5 on channel 1 */
     ok = ok && gi[5] == 0 && (gi[133] == 16384 || gi[133] == 16383) && gi[256 + 133] > 24500 && gi[256 + 133] < 24580 && gq[0] == 0;
+    sdr::GrabberBatch gr(8);
+    int16_t snap[512];
+    ok = ok && !gr.newDataAvailable(2) && !gr.grab(2, snap);
     std::printf("GPU_OK %d\n", (int)ok);
     return ok ? 0 : 2;
   } catch (const std::runtime_error &e) {

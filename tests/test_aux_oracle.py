@@ -91,7 +91,21 @@ def test_detector_decisions_do_not_hinge_on_fft_rounding():
     assert min(margins) > 1e-3  # decisions at least 0.2 % away from a threshold vs 2e-6 of FFT rounding
 
 
-def declared(prefixes=("sdr_preproc_", "sdr_iqgen_", "sdr_aux_")):
+def test_grabber_oracle_matches_reference_binary():
+    """SURVEY 8f row 3 (no arithmetic): the restatement against the unmodified AudioGrabberComplex256 for 1..9 blocks."""
+    if not A.ref_available():
+        pytest.skip("oracle/_ref/refaux not built (needs the reference tree)")
+    for nb in (1, 2, 3, 4, 9):
+        I, Q = S.pp_case(6, nb, seed=40 + nb)
+        o, f = A.grab_run(I, Q)
+        ro, rf = A.ref_grab_run(I, Q)
+        assert np.array_equal(o, ro) and np.array_equal(f, rf)
+        if nb >= 2:
+            last = (nb // 2) * 2   # blocks [last-2, last) form the snapshot
+            assert np.array_equal(o[:, 0::2], I[:, (last - 2) * 128: last * 128]) and np.array_equal(o[:, 1::2], Q[:, (last - 2) * 128: last * 128])
+
+
+def declared(prefixes=("sdr_preproc_", "sdr_iqgen_", "sdr_grabber_", "sdr_aux_")):
     src = open(os.path.join(ROOT, "include", "sdr_aux.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(n for n in re.findall(r"\b(sdr_\w+)\s*\(", src) if n.startswith(prefixes)))

@@ -263,3 +263,38 @@ def test_cpp_host_classes_run_on_the_gpu(aux, tmp_path):
                         "-Wl,-rpath," + os.path.dirname(lib)], check=True)
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 0 and "GPU_OK" in r.stdout and "NO_DEVICE" not in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("chunks", [(1,), (2,), (1, 2, 3), (5, 4)])
+def test_grabber_matches_oracle(aux, chunks):
+    """AudioGrabberComplex256: after every call, grab() must hand out what the reference's object would
+    after the same number of update() calls -- including 'nothing yet' and the new-data flag."""
+    import torch
+    from oracle import aux_lib as A
+    nch, nb = 37, 23
+    I, Q = S.pp_case(nch, nb, seed=77)
+    dI, dQ = _dev(I), _dev(Q)
+    g = aux.GrabberBatch(nch)
+    pos = k = 0
+    while pos < nb:
+        sz = min(chunks[k % len(chunks)], nb - pos); k += 1
+        g.process(dI[:, pos * 128:(pos + sz) * 128], dQ[:, pos * 128:(pos + sz) * 128], n_blocks=sz)
+        pos += sz
+        want, flags = A.grab_run(I[:, :pos * 128], Q[:, :pos * 128])
+        if k % 2 == 0 or pos == nb:   # grab on some calls only: the flag must survive the calls in between
+            pick = [0, 5, nch - 1]
+            fresh = [g.newDataAvailable(c) for c in pick]
+            got = g.grab(pick)
+            if flags[0, 1]:
+                assert got is not None and np.array_equal(got.astype(np.int32), want[pick])
+                assert not any(g.newDataAvailable(c) for c in pick)
+            else:
+                assert got is None and not any(fresh)
+    allc = g.grab()
+    want, _ = A.grab_run(I, Q)
+    assert np.array_equal(allc.astype(np.int32), want)
+    out = torch.zeros((nch, 512), dtype=torch.int16, device="cuda:0")
+    assert g.L.sdr_grabber_grab_device(g.h, out.data_ptr(), None) == 1
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().astype(np.int32), want)
+    g.close()
