@@ -210,14 +210,14 @@ class SdrBatch:
 
     def role_profile(self):
         """Per-stage busy fraction of the pipeline kernel (needs SDR_ROLE_PROFILE=1 at construction)."""
-        busy = np.zeros(24, np.uint64); total = np.zeros(2, np.uint64); groups = np.zeros(2, np.uint64)
+        busy = np.zeros(28, np.uint64); total = np.zeros(2, np.uint64); groups = np.zeros(2, np.uint64)
         self._check(self.L.sdr_batch_get_role_profile(self.h, busy.ctypes.data, total.ctypes.data, groups.ctypes.data))
-        names = [["in", "nb", "if_i", "if_q", "nco", "hil0", "hil1", "hil2", "hil3", "aud", "agc", "als_out"],
-                 ["in", "nb", "if_i", "if_q", "pll", "nco2", "img_i", "img_q", "mag", "aud", "agc", "als_out"]]
+        names = [["in", "nb_scan", "if_i", "if_q", "nco", "hil0", "hil1", "hil2", "hil3", "aud", "agc", "als_out", "envl", "nb_out"],
+                 ["in", "nb_scan", "if_i", "if_q", "pll", "nco2", "img_i", "img_q", "mag", "aud", "agc", "als_out", "envl", "nb_out"]]
         out = {}
         for cls, cname in enumerate(("ssb", "env")):
             if total[cls]:
-                out[cname] = {n: float(busy[cls * 12 + w]) / float(total[cls]) for w, n in enumerate(names[cls])}
+                out[cname] = {n: float(busy[cls * 14 + w]) / float(total[cls]) for w, n in enumerate(names[cls])}
                 out[cname]["cta_cycles_per_launch"] = float(total[cls]) / float(groups[cls])
         return out
 

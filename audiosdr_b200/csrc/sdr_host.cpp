@@ -400,10 +400,13 @@ int fold_profile(sdr_batch *h) {
   if (d2h(rows.data(), h->d_prof, rows.size() * 8, h->last_stream) || dev_sync(h->last_stream)) return SDR_ERR_CUDA;
   for (uint32_t g = 0; g < h->n_groups && g < h->h_groups.size(); g++) {
     int cls = h->h_groups[g].cls;
-    for (int w = 0; w < 12; w++) h->prof_busy[cls * 12 + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
-    h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + 12];
-    for (int e = 0; e < 8; e++) h->prof_extra[cls * 8 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 13 + e];
-    for (int e = 0; e < 13; e++) h->prof_load[cls * 13 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 24 + e];
+    /* row layout (sdr_kernel.cu pipeline_loop, Probe::flush): [0..13] busy per stage, [14] CTA pipeline cycles, [15] prologue,
+     * [16..29] state-load cycles per stage, [30..32] NB sub-phases, [33..35] IN sub-phases */
+    for (int w = 0; w < SDR_STAGES; w++) h->prof_busy[cls * SDR_STAGES + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
+    h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + 14];
+    for (int e = 0; e < 6; e++) h->prof_extra[cls * 8 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 30 + e];
+    for (int e = 0; e < SDR_STAGES; e++) h->prof_load[cls * (SDR_STAGES + 1) + e] += rows[(size_t)g * SDR_PROF_SLOTS + 16 + e];
+    h->prof_load[cls * (SDR_STAGES + 1) + SDR_STAGES] += rows[(size_t)g * SDR_PROF_SLOTS + 15];
     h->prof_groups[cls] += h->prof_launches;
   }
   if (dev_zero(h->d_prof, rows.size() * 8, h->last_stream)) return SDR_ERR_CUDA;
@@ -466,7 +469,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
-  h->prof_busy.assign(24, 0); h->prof_extra.assign(16, 0); h->prof_load.assign(26, 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
+  h->prof_busy.assign(2 * SDR_STAGES, 0); h->prof_extra.assign(16, 0); h->prof_load.assign(2 * (SDR_STAGES + 1), 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
   SdrTables *t = new SdrTables();
   const uint32_t *ifs[4] = {SDR_TAB_IF_SSB, SDR_TAB_IF_CW, SDR_TAB_IF_WSPR, SDR_TAB_IF_AM};
@@ -681,22 +684,22 @@ int sdr_batch_get_status(sdr_batch_t *h, const uint32_t *ids, uint32_t n, sdr_ch
   return SDR_OK;
 }
 
-int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy24, uint64_t *total2, uint64_t *groups2) {
-  if (!h || !busy24 || !total2 || !groups2) return fail(SDR_ERR_ARG, "get_role_profile: bad arguments");
+int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy28, uint64_t *total2, uint64_t *groups2) {
+  if (!h || !busy28 || !total2 || !groups2) return fail(SDR_ERR_ARG, "get_role_profile: bad arguments");
   if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
   if (fold_profile(h)) return SDR_ERR_CUDA;
-  for (int i = 0; i < 24; i++) busy24[i] = h->prof_busy[i];
+  for (int i = 0; i < 2 * SDR_STAGES; i++) busy28[i] = h->prof_busy[i];
   for (int i = 0; i < 2; i++) { total2[i] = h->prof_total[i]; groups2[i] = h->prof_groups[i]; }
   if (getenv("SDR_ROLE_PROFILE_NB"))
     for (int cls = 0; cls < 2; cls++)
       if (h->prof_groups[cls]) {
         fprintf(stderr, "[sdr] class %d: cycles per CTA launch: prologue %.0f, pipeline %.0f; state-load cycles per stage:", cls,
-                (double)h->prof_load[cls * 13 + 12] / h->prof_groups[cls], (double)h->prof_total[cls] / h->prof_groups[cls]);
-        for (int w = 0; w < 12; w++) fprintf(stderr, " %.0f", (double)h->prof_load[cls * 13 + w] / h->prof_groups[cls]);
+                (double)h->prof_load[cls * (SDR_STAGES + 1) + SDR_STAGES] / h->prof_groups[cls], (double)h->prof_total[cls] / h->prof_groups[cls]);
+        for (int w = 0; w < SDR_STAGES; w++) fprintf(stderr, " %.0f", (double)h->prof_load[cls * (SDR_STAGES + 1) + w] / h->prof_groups[cls]);
         fprintf(stderr, "\n");
       }
   if (getenv("SDR_ROLE_PROFILE_NB") && h->prof_total[0])
-    fprintf(stderr, "[sdr] sub-phase share of CTA time: nb.scan %.3f nb.edge %.3f nb.out %.3f | in.fetch %.3f in.ringst %.3f in.env %.3f\n",
+    fprintf(stderr, "[sdr] sub-phase share of CTA time: nb.wait %.3f nb.scan %.3f nb.edge+request %.3f | in.wait %.3f in.scale+ring %.3f (unused %.3f)\n",
             (double)h->prof_extra[0] / h->prof_total[0], (double)h->prof_extra[1] / h->prof_total[0], (double)h->prof_extra[2] / h->prof_total[0],
             (double)h->prof_extra[3] / h->prof_total[0], (double)h->prof_extra[4] / h->prof_total[0], (double)h->prof_extra[5] / h->prof_total[0]);
   return SDR_OK;

@@ -1,6 +1,6 @@
 /* sdr_kernel.cu -- sm_100a kernels of the batched receiver chain and their launchers.
  *
- * sdr_pipeline_kernel: one CTA per 32-channel group, 11 warps = 11 pipeline stages (see
+ * sdr_pipeline_kernel: one CTA per 32-channel group, 14 warps = 14 pipeline stages (see
  * sdr_pipeline.cuh).  Build flags matter for parity: -fmad=false (no FMA contraction; the reference
  * rounds every product and sum separately), IEEE division and square root (nvcc defaults), no FTZ.
  */
@@ -42,14 +42,14 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n
   if (prof && (threadIdx.x & 31) == 0) {
     unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
     row[role] += (unsigned long long)busy;
-    row[24 + role] += (unsigned long long)(t_loaded - x.t0);                 /* this stage's state load */
-    if (threadIdx.x == 0) { row[12] += (unsigned long long)(clock64() - t_begin); row[36] += (unsigned long long)(t_begin - x.t0); }
+    row[16 + role] += (unsigned long long)(t_loaded - x.t0);                 /* this stage's state load */
+    if (threadIdx.x == 0) { row[14] += (unsigned long long)(clock64() - t_begin); row[15] += (unsigned long long)(t_begin - x.t0); }
   }
 }
 
 /* One warp = one stage.  Stages common to both pipeline classes are instantiated once (offsets and delays
  * are run-time values) to keep the kernel's instruction footprint small: every warp runs different code, so
- * the hot loops of all 12 stages have to share the instruction caches. */
+ * the hot loops of all 14 stages have to share the instruction caches. */
 __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
   const uint32_t n = x.L->n_tiles;
   const bool ssb = x.G->cls == CLS_SSB;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     const int dst = is_if ? (int)S_Y : (is_aud ? (ssb ? (int)S_B : (int)E_B) : (int)E_V); /* audio and image filters work in place */
     const int s_per = is_aud ? 1 : 2, d_per = is_aud ? 1 : 2;
     const int a_cyc = ssb ? (int)NA : (int)NB_RING;
-    const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : a_cyc), d_cyc = is_img ? (int)NZ2 : (is_aud ? a_cyc : 2);
+    const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : a_cyc), d_cyc = s_cyc; /* all three kinds filter in place */
     const int delay = is_if ? (int)D_IF : (is_aud ? (ssb ? (int)D_AUD : (int)E_D_AUD) : (int)E_D_IMG);
     RoleBiquad r; r.load(x, lane, kind, rail);
     pipeline_loop(x, warp, n, delay, dmax, [&](uint32_t t) {
@@ -80,6 +80,8 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
       r.save(x, lane);
     } break;
     case 1: { RoleNb r; r.load(x, lane); pipeline_loop(x, warp, n, D_NB, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case 12: { RoleEnvl r; r.load(x, lane); pipeline_loop(x, warp, n, D_ENVL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); } break;
+    case 13: { RoleNbo r; r.load(x, lane); pipeline_loop(x, warp, n, D_NBO, dmax, [&](uint32_t t) { r.step(x, lane, t); }); } break;
     case 10: {
       RoleAgc r; r.load(x, lane);
       const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? (int)NA : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
@@ -142,14 +144,15 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
     if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
   }
   /* Physical warp -> stage.  The warp scheduler of an SM sub-partition favours the HIGHER warp id among eligible
-   * warps (and warp id % 4 picks the sub-partition), so the latency-bound serial stages (blanker, input, AGC,
-   * output / PLL) get the highest ids and the throughput stages with plenty of independent work (the four Hilbert
-   * warps, one per sub-partition) the lowest: the serial chains issue the moment they are ready and the FIR fills
-   * every other slot.  Stage numbering (the `warp` argument of run_group): 0 IN, 1 NB, 2/3 IF-I/IF-Q,
-   * 4..8 class specific (SSB: NCO, Hilbert x4; ENV: PLL, NCO2, image I/Q, envelope), 9 audio BPF, 10 AGC, 11 ALS+OUT. */
+   * warps (and warp id % 4 picks the sub-partition), so inside each sub-partition the latency-bound serial stages get
+   * the highest ids and a Hilbert warp (plenty of independent work) the lowest: the serial chains issue the moment they
+   * are ready and the FIR fills every other slot; the estimated stage loads are spread evenly over the four
+   * sub-partitions (two of them hold four warps, two hold three).  Stage numbering (the `warp` argument of
+   * run_group): 0 IN, 1 NB scan, 2/3 IF-I/IF-Q, 4..8 class specific (SSB: NCO, Hilbert x4; ENV: PLL, NCO2, image I/Q,
+   * envelope), 9 audio BPF, 10 AGC, 11 ALS+OUT, 12 ENVL, 13 NB-out. */
   const int phys = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  /* SSB: {5,6,7,8, 2,3,9,4, 1,0,10,11}   ENV: {6,7,5,8, 2,3,9,11, 1,0,10,4}   (4 bits per entry, no local array) */
-  const unsigned long long map_ssb = 0xBA0149328765ull, map_env = 0x4A01B9328576ull;
+  /* SSB: {5,6,7,8, 2,3,11,4, 9,12,10,1, 0,13}   ENV: {7,1,5,8, 2,3,6,11, 9,12,4,10, 0,13}   (4 bits per entry, no local array) */
+  const unsigned long long map_ssb = 0xD01AC94B328765ull, map_env = 0xD0A4C9B6328517ull;
   const int stage = (int)(((x.G->cls == CLS_SSB ? map_ssb : map_env) >> (4 * phys)) & 15);
   run_group(x, stage, lane);
 }

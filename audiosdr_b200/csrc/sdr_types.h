@@ -114,6 +114,7 @@ typedef struct {
   unsigned long long *prof; /* optional [n_groups][SDR_PROF_SLOTS]: busy cycles per warp role + CTA total (diagnostics) */
 } SdrLaunch;
 
+#define SDR_STAGES 14     /* pipeline stages = warps per CTA */
 #define SDR_PROF_SLOTS 40
 
 #define SDR_AGC_LUT_STRIDE 132

@@ -164,8 +164,9 @@ int sdr_batch_peek_state(sdr_batch_t *h, uint32_t channel, uint32_t word, float 
 
 /* Diagnostics: per-stage busy cycles of the pipeline kernel, summed over groups and launches since create.
  * Only recorded when the environment variable SDR_ROLE_PROFILE=1 was set at create (costs two clock reads per
- * stage per tile).  busy[cls*12 + warp], total[cls] = summed CTA cycles, groups[cls] = CTA launches counted. */
-int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy24, uint64_t *total2, uint64_t *groups2);
+ * stage per tile).  busy[cls*14 + stage] (14 stages per pipeline class), total[cls] = summed CTA cycles,
+ * groups[cls] = CTA launches counted. */
+int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy28, uint64_t *total2, uint64_t *groups2);
 
 /* Kernels this handle has launched so far (for the benchmark's gpu_launches claim). */
 uint64_t sdr_batch_launch_count(const sdr_batch_t *h);

@@ -26,11 +26,12 @@ namespace {
 struct Warp {
   std::vector<RoleIn> in; std::vector<RoleNb> nbk; std::vector<RoleBiquad> bq; std::vector<RoleNco> nco; std::vector<RoleHilbert> hil;
   std::vector<RoleAgc> agc; std::vector<RoleOut> out; std::vector<RolePll> pll; std::vector<RoleNco2> nco2; std::vector<RoleMag> mag;
+  std::vector<RoleEnvl> envl; std::vector<RoleNbo> nbo;
 };
 
 int delay_of(int cls, int w) {
-  static const int ssb[12] = {D_IN, D_NB, D_IF, D_IF, D_NCO, D_HIL, D_HIL, D_HIL, D_HIL, D_AUD, D_AGC, D_OUT};
-  static const int env[12] = {D_IN, D_NB, D_IF, D_IF, E_D_PLL, E_D_NCO2, E_D_IMG, E_D_IMG, E_D_MAG, E_D_AUD, E_D_AGC, E_D_OUT};
+  static const int ssb[14] = {D_IN, D_NB, D_IF, D_IF, D_NCO, D_HIL, D_HIL, D_HIL, D_HIL, D_AUD, D_AGC, D_OUT, D_ENVL, D_NBO};
+  static const int env[14] = {D_IN, D_NB, D_IF, D_IF, E_D_PLL, E_D_NCO2, E_D_IMG, E_D_IMG, E_D_MAG, E_D_AUD, E_D_AGC, E_D_OUT, D_ENVL, D_NBO};
   return cls == CLS_SSB ? ssb[w] : env[w];
 }
 
@@ -42,10 +43,12 @@ void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
   const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
   if (w == 0) { k.in.resize(32); RoleIn &r = k.in[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step_a(x, lane, t); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane); }
   else if (w == 1) { k.nbk.resize(32); RoleNb &r = k.nbk[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }
+  else if (w == 12) { k.envl.resize(32); RoleEnvl &r = k.envl[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); }
+  else if (w == 13) { k.nbo.resize(32); RoleNbo &r = k.nbo[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); }
   else if (w == 2 || w == 3) {
     k.bq.resize(32); RoleBiquad &r = k.bq[lane]; const int rail = w - 2;
     if (phase == 0) r.load(x, lane, 0, rail);
-    else if (phase == 1) r.step(x.tile(S_X, (t % NR) * 2 + rail), x.tile(S_Y, (t & 1) * 2 + rail), lane, true);
+    else if (phase == 1) r.step(x.tile(S_X, (t % NR) * 2 + rail), x.tile(S_Y, (t % NR) * 2 + rail), lane, true);
     else r.save(x, 0, rail);
   } else if (w == 9) {
     k.bq.resize(32); RoleBiquad &r = k.bq[lane];

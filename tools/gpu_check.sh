@@ -14,7 +14,7 @@ python - <<PY
 import json
 try:
     lines=open('gpurun_out/${TAG}_roles.json').read().strip().splitlines()
-    d=json.loads(lines[-1]); rp=d['role_profile']['ssb']; cyc=rp.pop('cta_cycles_per_launch'); steps=d['config']['blocks_per_step']*4+7
+    d=json.loads(lines[-1]); rp=d['role_profile']['ssb']; cyc=rp.pop('cta_cycles_per_launch'); steps=d['config']['blocks_per_step']*4+8
     print('role profile: %.0f Msps, cycles/step %.0f, busy kcycles/tile:'%(d['value'],cyc/steps), {k:round(v*cyc/steps/1000,1) for k,v in rp.items()})
     print([l for l in lines if l.startswith('[sdr]')])
 except Exception as e: print('role profile failed', e)
