@@ -543,6 +543,17 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
   if ((rc = sync_config(h, stream)) != 0) return rc;
   SdrLaunch L;
   memset(&L, 0, sizeof L);
+  L.map_ssb = SDR_MAP_SSB_DEFAULT; L.map_env = SDR_MAP_ENV_DEFAULT;
+  { /* diagnostics: alternative stage placement; a map must name each of the 14 stages exactly once */
+    const char *names[2] = {"SDR_MAP_SSB", "SDR_MAP_ENV"};
+    unsigned long long *dst[2] = {&L.map_ssb, &L.map_env};
+    for (int k = 0; k < 2; k++) if (const char *e = getenv(names[k])) {
+      const unsigned long long m = strtoull(e, nullptr, 16);
+      unsigned seen = 0;
+      for (int w = 0; w < SDR_STAGES; w++) seen |= 1u << ((m >> (4 * w)) & 15);
+      if (seen == (1u << SDR_STAGES) - 1) *dst[k] = m;
+    }
+  }
   L.in_i = I; L.in_q = Q; L.out = audio; L.in_pitch = in_pitch; L.out_pitch = out_pitch; L.in_fmt = in_fmt; L.out_fmt = out_fmt;
   L.n_tiles = n_blocks * SDR_TPB; L.blk0_mod3 = (uint32_t)(h->blocks_done % 3);
   L.cfg = h->d_cfg; L.state = h->d_state; L.ch_stride = h->ch_stride; L.groups = h->d_groups; L.agc_luts = h->d_luts; L.tabs = h->d_tabs;

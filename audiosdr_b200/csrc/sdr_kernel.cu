@@ -145,15 +145,15 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
   }
   /* Physical warp -> stage.  The warp scheduler of an SM sub-partition favours the HIGHER warp id among eligible
    * warps (and warp id % 4 picks the sub-partition), so inside each sub-partition the latency-bound serial stages get
-   * the highest ids and a Hilbert warp (plenty of independent work) the lowest: the serial chains issue the moment they
-   * are ready and the FIR fills every other slot; the estimated stage loads are spread evenly over the four
-   * sub-partitions (two of them hold four warps, two hold three).  Stage numbering (the `warp` argument of
+   * a high id issue the moment they are ready (two sub-partitions hold four warps, two hold three).  Stage numbering (the `warp` argument of
    * run_group): 0 IN, 1 NB scan, 2/3 IF-I/IF-Q, 4..8 class specific (SSB: NCO, Hilbert x4; ENV: PLL, NCO2, image I/Q,
    * envelope), 9 audio BPF, 10 AGC, 11 ALS+OUT, 12 ENVL, 13 NB-out. */
   const int phys = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  /* SSB: {5,6,7,8, 2,3,11,4, 9,12,10,1, 0,13}   ENV: {7,1,5,8, 2,3,6,11, 9,12,4,10, 0,13}   (4 bits per entry, no local array) */
-  const unsigned long long map_ssb = 0xD01AC94B328765ull, map_env = 0xD0A4C9B6328517ull;
-  const int stage = (int)(((x.G->cls == CLS_SSB ? map_ssb : map_env) >> (4 * phys)) & 15);
+  /* The default placements (sdr_types.h) were found by measurement (tools/map_search.py, hill climbing over pair swaps with
+   * CUDA-event timing of the bench workload): SSB 0x3BADC548961720 = sub-partition 0 {IN, Hilbert, Hilbert, OUT},
+   * 1 {IF-I, audio BPF, ENVL, IF-Q}, 2 {Hilbert, Hilbert, NB-out}, 3 {NB scan, NCO, AGC} -- 16 % faster than a placement
+   * balanced by instruction count: the short latency-bound chains (blanker scan, AGC) want a sub-partition to themselves. */
+  const int stage = (int)(((x.G->cls == CLS_SSB ? L.map_ssb : L.map_env) >> (4 * phys)) & 15);
   run_group(x, stage, lane);
 }
 

@@ -112,7 +112,13 @@ typedef struct {
   uint32_t n_groups;
   uint32_t pad;
   unsigned long long *prof; /* optional [n_groups][SDR_PROF_SLOTS]: busy cycles per warp role + CTA total (diagnostics) */
+  unsigned long long map_ssb, map_env; /* physical warp -> stage, 4 bits per warp (see sdr_kernel.cu) */
 } SdrLaunch;
+
+/* default placement of the 14 stages on the 14 warps of a CTA (warp id % 4 = SM sub-partition, higher id = preferred by the
+ * scheduler); SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */
+#define SDR_MAP_SSB_DEFAULT 0x3BADC548961720ull
+#define SDR_MAP_ENV_DEFAULT 0xD0A4C9B6328517ull
 
 #define SDR_STAGES 14     /* pipeline stages = warps per CTA */
 #define SDR_PROF_SLOTS 40
