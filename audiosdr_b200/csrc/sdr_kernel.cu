@@ -144,8 +144,8 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
     if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
   }
   /* Physical warp -> stage.  The warp scheduler of an SM sub-partition favours the HIGHER warp id among eligible
-   * warps (and warp id % 4 picks the sub-partition), so inside each sub-partition the latency-bound serial stages get
-   * a high id issue the moment they are ready (two sub-partitions hold four warps, two hold three).  Stage numbering (the `warp` argument of
+   * warps, and warp id % 4 picks the sub-partition (two of them hold four warps, two hold three), so the placement
+   * decides which stages compete for one scheduler and who wins.  Stage numbering (the `warp` argument of
    * run_group): 0 IN, 1 NB scan, 2/3 IF-I/IF-Q, 4..8 class specific (SSB: NCO, Hilbert x4; ENV: PLL, NCO2, image I/Q,
    * envelope), 9 audio BPF, 10 AGC, 11 ALS+OUT, 12 ENVL, 13 NB-out. */
   const int phys = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -118,7 +118,7 @@ typedef struct {
 /* default placement of the 14 stages on the 14 warps of a CTA (warp id % 4 = SM sub-partition, higher id = preferred by the
  * scheduler); SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */
 #define SDR_MAP_SSB_DEFAULT 0x3BADC548961720ull
-#define SDR_MAP_ENV_DEFAULT 0xD0A4C9B6328517ull
+#define SDR_MAP_ENV_DEFAULT 0xA0D459B1328C67ull
 
 #define SDR_STAGES 14     /* pipeline stages = warps per CTA */
 #define SDR_PROF_SLOTS 40
