@@ -63,12 +63,14 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     const int dst = is_if ? (int)S_Y : (is_aud ? (ssb ? (int)S_B : (int)E_B) : (int)E_V); /* audio and image filters work in place */
     const int s_per = is_aud ? 1 : 2, d_per = is_aud ? 1 : 2;
     const int a_cyc = ssb ? (int)NA : (int)NB_RING;
-    const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : a_cyc), d_cyc = s_cyc; /* all three kinds filter in place */
+    const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : a_cyc); /* all three kinds filter in place: source cycle = destination cycle */
     const int delay = is_if ? (int)D_IF : (is_aud ? (ssb ? (int)D_AUD : (int)E_D_AUD) : (int)E_D_IMG);
     RoleBiquad r; r.load(x, lane, kind, rail);
+    int slot = 0; /* t % s_cyc, counted (the stage's tiles are t = 0, 1, 2, ...; the cycle length is a run-time value) */
     pipeline_loop(x, warp, n, delay, dmax, [&](uint32_t t) {
       const bool run = is_if ? true : (is_aud ? r.on : (r.cid >= 0 && env_flag(x, lane, t) != 0));
-      r.step(x.tile(src, (int)(t % s_cyc) * s_per + rail), x.tile(dst, (int)(t % d_cyc) * d_per + rail), lane, run);
+      r.step(x.tile(src, slot * s_per + rail), x.tile(dst, slot * d_per + rail), lane, run);
+      slot = slot + 1 == s_cyc ? 0 : slot + 1;
     });
     r.save(x, kind, rail);
     return;
