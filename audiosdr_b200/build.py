@@ -36,7 +36,8 @@ def build_library(force=False, verbose=False):
     """Builds audiosdr_b200/libsdr_batch.so; returns its path."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    # SDR_NVCC_EXTRA: extra -D switches for A/B builds of kernel variants (tools/gpu_ab.sh); unset for the product
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("SDR_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) if not s.endswith(".cpp") else os.path.join(CSRC, s) for s in SOURCES]
     # sdr_host.cpp is plain C++ that calls the CUDA runtime: compile it as CUDA so that one nvcc call links everything
     cmd = [c for c in cmd]

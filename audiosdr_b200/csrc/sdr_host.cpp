@@ -152,7 +152,7 @@ struct sdr_batch {
   void *s_h2d, *s_comp, *s_d2h; void *ev_h2d[2], *ev_comp[2], *ev_d2h[2];
   uint32_t n_groups;
   unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
-  std::vector<uint64_t> prof_busy, prof_total, prof_groups, prof_extra, prof_load; /* folded per class */
+  std::vector<uint64_t> prof_busy, prof_total, prof_groups, prof_extra, prof_load, prof_crit, prof_bar; /* folded per class */
   uint64_t blocks_done, launches;
   void *last_stream;
   std::vector<SdrChanCfg> h_cfg;
@@ -401,12 +401,15 @@ int fold_profile(sdr_batch *h) {
   for (uint32_t g = 0; g < h->n_groups && g < h->h_groups.size(); g++) {
     int cls = h->h_groups[g].cls;
     /* row layout (sdr_kernel.cu pipeline_loop, Probe::flush): [0..13] busy per stage, [14] CTA pipeline cycles, [15] prologue,
-     * [16..29] state-load cycles per stage, [30..32] NB sub-phases, [33..35] IN sub-phases */
+     * [16..29] state-load cycles per stage, [30..32] NB sub-phases, [33..35] IN sub-phases, [40..53] steps in which the stage was
+     * the last to finish, [54] sum over steps of the slowest stage's busy cycles, [55] steps */
     for (int w = 0; w < SDR_STAGES; w++) h->prof_busy[cls * SDR_STAGES + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
     h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + 14];
     for (int e = 0; e < 6; e++) h->prof_extra[cls * 8 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 30 + e];
     for (int e = 0; e < SDR_STAGES; e++) h->prof_load[cls * (SDR_STAGES + 1) + e] += rows[(size_t)g * SDR_PROF_SLOTS + 16 + e];
     h->prof_load[cls * (SDR_STAGES + 1) + SDR_STAGES] += rows[(size_t)g * SDR_PROF_SLOTS + 15];
+    for (int e = 0; e < 16; e++) h->prof_crit[cls * 16 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 40 + e];
+    for (int e = 0; e < SDR_STAGES; e++) h->prof_bar[cls * SDR_STAGES + e] += rows[(size_t)g * SDR_PROF_SLOTS + 64 + e];
     h->prof_groups[cls] += h->prof_launches;
   }
   if (dev_zero(h->d_prof, rows.size() * 8, h->last_stream)) return SDR_ERR_CUDA;
@@ -469,7 +472,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
-  h->prof_busy.assign(2 * SDR_STAGES, 0); h->prof_extra.assign(16, 0); h->prof_load.assign(2 * (SDR_STAGES + 1), 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
+  h->prof_busy.assign(2 * SDR_STAGES, 0); h->prof_crit.assign(32, 0); h->prof_bar.assign(2 * SDR_STAGES, 0); h->prof_extra.assign(16, 0); h->prof_load.assign(2 * (SDR_STAGES + 1), 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
   SdrTables *t = new SdrTables();
   const uint32_t *ifs[4] = {SDR_TAB_IF_SSB, SDR_TAB_IF_CW, SDR_TAB_IF_WSPR, SDR_TAB_IF_AM};
@@ -566,6 +569,7 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
       h->prof_cap = need;
     }
     L.prof = h->d_prof; h->prof_launches++;
+    if (const char *e = getenv("SDR_DIAG_SKIP")) L.diag_skip = (uint32_t)strtoul(e, nullptr, 16); /* time stages in isolation */
   }
   int e = sdrk_launch_pipeline(&L, stream);
   if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
@@ -707,6 +711,17 @@ int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy28, uint64_t *total
         fprintf(stderr, "[sdr] class %d: cycles per CTA launch: prologue %.0f, pipeline %.0f; state-load cycles per stage:", cls,
                 (double)h->prof_load[cls * (SDR_STAGES + 1) + SDR_STAGES] / h->prof_groups[cls], (double)h->prof_total[cls] / h->prof_groups[cls]);
         for (int w = 0; w < SDR_STAGES; w++) fprintf(stderr, " %.0f", (double)h->prof_load[cls * (SDR_STAGES + 1) + w] / h->prof_groups[cls]);
+        fprintf(stderr, "\n");
+      }
+  if (getenv("SDR_ROLE_PROFILE_NB"))
+    for (int cls = 0; cls < 2; cls++)
+      if (h->prof_crit[cls * 16 + 15]) {
+        const double steps = (double)h->prof_crit[cls * 16 + 15];
+        fprintf(stderr, "[sdr] class %d: slowest stage of a step: mean %.0f cycles; share of steps in which each stage was the slowest:", cls,
+                (double)h->prof_crit[cls * 16 + 14] / steps);
+        for (int w = 0; w < SDR_STAGES; w++) fprintf(stderr, " %.3f", (double)h->prof_crit[cls * 16 + w] / steps);
+        fprintf(stderr, "\n[sdr] class %d: cycles per step at the barrier, per stage:", cls);
+        for (int w = 0; w < SDR_STAGES; w++) fprintf(stderr, " %.0f", (double)h->prof_bar[cls * SDR_STAGES + w] / steps);
         fprintf(stderr, "\n");
       }
   if (getenv("SDR_ROLE_PROFILE_NB") && h->prof_total[0])

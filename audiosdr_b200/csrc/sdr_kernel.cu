@@ -24,24 +24,36 @@ __device__ __forceinline__ void step_barrier() {
 
 template <class Body>
 __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n_tiles, int delay, int dmax, Body body) {
-  unsigned long long *prof = x.L->prof;
+  unsigned long long *prof = x.prof ? x.L->prof : nullptr; /* nullptr at compile time in the product kernel */
   const long long t_loaded = prof ? clock64() : 0;
   step_barrier(); /* histories and tables are in shared memory */
   const uint32_t steps = n_tiles + (uint32_t)dmax;
-  long long busy = 0, t_begin = prof ? clock64() : 0;
+  long long busy = 0, at_barrier = 0, t_begin = prof ? clock64() : 0;
+  uint32_t *scr = reinterpret_cast<uint32_t *>(x.smem + S_PROFSCR);
 #pragma unroll 1
   for (uint32_t s = 0; s < steps; s++) {
     const long long tau = (long long)s - delay;
-    if (tau >= 0 && tau < (long long)n_tiles) {
+    long long b = 0;
+    if (tau >= 0 && tau < (long long)n_tiles && !(prof && ((x.L->diag_skip >> role) & 1u))) {
       const long long t0 = prof ? clock64() : 0;
       body((uint32_t)tau);
-      if (prof) busy += clock64() - t0;
+      if (prof) { b = clock64() - t0; busy += b; }
     }
+    if (prof && (threadIdx.x & 31) == 0) scr[(s & 1) * 16 + role] = (uint32_t)b;
+    const long long tb = prof ? clock64() : 0;
     step_barrier();
+    if (prof) at_barrier += clock64() - tb;
+    if (prof && role == 0 && (threadIdx.x & 31) == 0) { /* which stage did this step wait for? */
+      uint32_t mx = 0; int arg = 0;
+      for (int w = 0; w < SDR_STAGES; w++) { const uint32_t v = scr[(s & 1) * 16 + w]; if (v > mx) { mx = v; arg = w; } }
+      unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
+      row[40 + arg] += 1; row[54] += mx; row[55] += 1;
+    }
   }
   if (prof && (threadIdx.x & 31) == 0) {
     unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
     row[role] += (unsigned long long)busy;
+    row[64 + role] += (unsigned long long)at_barrier;                          /* cycles between this stage's arrival at the step barriers and its release */
     row[16 + role] += (unsigned long long)(t_loaded - x.t0);                 /* this stage's state load */
     if (threadIdx.x == 0) { row[14] += (unsigned long long)(clock64() - t_begin); row[15] += (unsigned long long)(t_begin - x.t0); }
   }
@@ -130,14 +142,15 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel(const __grid_constant__ SdrLaunch L) {
-  extern __shared__ __align__(16) unsigned char smem[];
+template <bool PROF>
+__device__ __forceinline__ void pipeline_cta(const SdrLaunch &L, unsigned char *smem) {
   Ctx x;
   x.L = &L;
   x.G = &L.groups[blockIdx.x];
   x.smem = smem;
   x.gidx = (int)blockIdx.x;
-  x.t0 = L.prof ? clock64() : 0;
+  x.prof = PROF;
+  x.t0 = PROF ? clock64() : 0;
   for (int i = threadIdx.x; i < 257; i += SDR_THREADS) x.f(S_SINE)[i] = L.tabs->sine[i];
   if (threadIdx.x < SDR_LANES) reinterpret_cast<int *>(smem + S_CID)[threadIdx.x] = x.G->cid[threadIdx.x];
   __syncthreads(); /* stage IN requests its first tile from load(), which needs the channel ids */
@@ -157,6 +170,18 @@ extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel
    * balanced by instruction count: the short latency-bound chains (blanker scan, AGC) want a sub-partition to themselves. */
   const int stage = (int)(((x.G->cls == CLS_SSB ? L.map_ssb : L.map_env) >> (4 * phys)) & 15);
   run_group(x, stage, lane);
+}
+
+/* The product kernel and its diagnostics twin (per-stage busy counters, sub-phase timers, stage skipping): the twin is
+ * launched only when the handle was created with SDR_ROLE_PROFILE=1.  Keeping the counters out of the product kernel is
+ * not cosmetic: its stages are 14 different instruction streams whose loops must share the instruction caches. */
+extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel(const __grid_constant__ SdrLaunch L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  pipeline_cta<false>(L, smem);
+}
+extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_prof_kernel(const __grid_constant__ SdrLaunch L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  pipeline_cta<true>(L, smem);
 }
 
 /* Zero (or re-seed) state words of listed channels: the side effects of the reference setters that
@@ -202,12 +227,15 @@ extern "C" int sdrk_setup_device(const float *hilbert64) {
   cudaError_t e = cudaMemcpyToSymbol(c_hilbert, hilbert64, 64 * sizeof(float));
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(sdr_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDR_SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(sdr_pipeline_prof_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDR_SMEM_BYTES);
   return (int)e;
 }
 
 extern "C" int sdrk_launch_pipeline(const SdrLaunch *L, void *stream) {
   if (L->n_groups == 0) return 0;
-  sdr_pipeline_kernel<<<L->n_groups, SDR_THREADS, SDR_SMEM_BYTES, (cudaStream_t)stream>>>(*L);
+  if (L->prof) sdr_pipeline_prof_kernel<<<L->n_groups, SDR_THREADS, SDR_SMEM_BYTES, (cudaStream_t)stream>>>(*L);
+  else sdr_pipeline_kernel<<<L->n_groups, SDR_THREADS, SDR_SMEM_BYTES, (cudaStream_t)stream>>>(*L);
   return (int)cudaGetLastError();
 }
 

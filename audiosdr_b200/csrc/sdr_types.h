@@ -110,7 +110,7 @@ typedef struct {
   const float *agc_luts; /* [n_luts][132] */
   const SdrTables *tabs;
   uint32_t n_groups;
-  uint32_t pad;
+  uint32_t diag_skip;    /* diagnostics (profiling runs only): bit w set = stage w idles; results are then meaningless */
   unsigned long long *prof; /* optional [n_groups][SDR_PROF_SLOTS]: busy cycles per warp role + CTA total (diagnostics) */
   unsigned long long map_ssb, map_env; /* physical warp -> stage, 4 bits per warp (see sdr_kernel.cu) */
 } SdrLaunch;
@@ -121,7 +121,7 @@ typedef struct {
 #define SDR_MAP_ENV_DEFAULT 0xA0D459B1328C67ull
 
 #define SDR_STAGES 14     /* pipeline stages = warps per CTA */
-#define SDR_PROF_SLOTS 40
+#define SDR_PROF_SLOTS 96
 
 #define SDR_AGC_LUT_STRIDE 132
 

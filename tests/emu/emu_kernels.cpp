@@ -97,7 +97,7 @@ void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
 
 void run_group(const SdrLaunch &L, const SdrGroup &G, bool reverse) {
   std::vector<unsigned char> smem(SDR_SMEM_BYTES, 0xFF);
-  Ctx x; x.L = &L; x.G = &G; x.smem = smem.data(); x.gidx = 0; x.t0 = 0;
+  Ctx x; x.L = &L; x.G = &G; x.smem = smem.data(); x.gidx = 0; x.t0 = 0; x.prof = false;
   for (int i = 0; i < 257; i++) x.f(S_SINE)[i] = L.tabs->sine[i];
   for (int i = 0; i < 32; i++) reinterpret_cast<int *>(smem.data() + S_CID)[i] = G.cid[i];
   for (int i = 0; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i++) {
