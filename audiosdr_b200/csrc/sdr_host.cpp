@@ -482,6 +482,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   for (int s = 0; s < 10; s++) for (int i = 0; i < 20; i++) t->aud_sets[s][i] = tabf(auds[s], i);
   for (int i = 0; i < 20; i++) t->am_image[i] = tabf(SDR_TAB_AM_IMAGE, i);
   for (int i = 0; i < 64; i++) t->hilbert[i] = tabf(SDR_TAB_HILBERT, i);
+  { const float k[8] = {1.0f, 1.0f, -1.0f, -1.0f, -0.0f, -0.0f, 0.0f, 0.0f}; memcpy(t->pk_consts, k, sizeof k); }
   memset(t->sine, 0, sizeof t->sine);
   for (int i = 0; i < 257; i++) t->sine[i] = tabf(SDR_TAB_SINE, i);
 

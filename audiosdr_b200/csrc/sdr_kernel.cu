@@ -12,7 +12,7 @@
 
 using namespace sdrk;
 
-__constant__ float c_hilbert[64]; /* compact Hilbert half, H:757-774: constant-bank operands of the unrolled FIR */
+__constant__ float2 c_hilbert2[64]; /* compact Hilbert half, H:757-774, every tap twice: the multiplicand pairs of the packed FIR */
 
 /* CTA-wide step barrier.  Every warp is a different stage and reaches the barrier from a different instruction, so the
  * unaligned form (`barrier.sync`, sm_70+) is used after re-converging the warp: lanes of an incompletely filled group
@@ -29,7 +29,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n
   step_barrier(); /* histories and tables are in shared memory */
   const uint32_t steps = n_tiles + (uint32_t)dmax;
   long long busy = 0, at_barrier = 0, t_begin = prof ? clock64() : 0;
-  uint32_t *scr = reinterpret_cast<uint32_t *>(x.smem + S_PROFSCR);
+  uint16_t *scr = reinterpret_cast<uint16_t *>(x.smem + S_PROFSCR);
 #pragma unroll 1
   for (uint32_t s = 0; s < steps; s++) {
     const long long tau = (long long)s - delay;
@@ -39,13 +39,13 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n
       body((uint32_t)tau);
       if (prof) { b = clock64() - t0; busy += b; }
     }
-    if (prof && (threadIdx.x & 31) == 0) scr[(s & 1) * 16 + role] = (uint32_t)b;
+    if (prof && (threadIdx.x & 31) == 0) scr[(s & 1) * 16 + role] = (uint16_t)(b >> 4);
     const long long tb = prof ? clock64() : 0;
     step_barrier();
     if (prof) at_barrier += clock64() - tb;
     if (prof && role == 0 && (threadIdx.x & 31) == 0) { /* which stage did this step wait for? */
       uint32_t mx = 0; int arg = 0;
-      for (int w = 0; w < SDR_STAGES; w++) { const uint32_t v = scr[(s & 1) * 16 + w]; if (v > mx) { mx = v; arg = w; } }
+      for (int w = 0; w < SDR_STAGES; w++) { const uint32_t v = (uint32_t)scr[(s & 1) * 16 + w] << 4; if (v > mx) { mx = v; arg = w; } }
       unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
       row[40 + arg] += 1; row[54] += mx; row[55] += 1;
     }
@@ -99,9 +99,11 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
     case 10: {
       RoleAgc r; r.load(x, lane);
       const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? (int)NA : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
+      int ss = 0, ds = 0; /* t % ns and t % NC, counted (ns is a run-time value) */
       pipeline_loop(x, warp, n, ssb ? (int)D_AGC : (int)E_D_AGC, dmax, [&](uint32_t t) {
         const float carrier = ssb ? 0.0f : x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane];
-        r.step(x.tile(src, t % ns), x.tile(dst, t % NC), lane, carrier);
+        r.step(x.tile(src, ss), x.tile(dst, ds), lane, carrier);
+        ss = ss + 1 == ns ? 0 : ss + 1; ds = ds + 1 == (int)NC ? 0 : ds + 1;
       });
       r.save(x);
     } break;
@@ -130,7 +132,7 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
         } else {
           const int sub = warp - 5;
           RoleHilbert r; r.load(x, lane, sub);
-          pipeline_loop(x, warp, n, D_HIL, dmax, [&](uint32_t t) { r.step(x, c_hilbert, lane, sub, t); });
+          pipeline_loop(x, warp, n, D_HIL, dmax, [&](uint32_t t) { r.step(x, reinterpret_cast<const float *>(c_hilbert2), lane, sub, t); });
           r.save(x, lane, sub);
         }
       } else {
@@ -224,7 +226,9 @@ extern "C" __global__ void sdr_gather_kernel(const float *state, unsigned long l
 }
 
 extern "C" int sdrk_setup_device(const float *hilbert64) {
-  cudaError_t e = cudaMemcpyToSymbol(c_hilbert, hilbert64, 64 * sizeof(float));
+  float2 h2[64];
+  for (int i = 0; i < 64; i++) h2[i] = make_float2(hilbert64[i], hilbert64[i]);
+  cudaError_t e = cudaMemcpyToSymbol(c_hilbert2, h2, sizeof h2);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(sdr_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDR_SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;

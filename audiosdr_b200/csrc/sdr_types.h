@@ -94,6 +94,7 @@ typedef struct {
   float am_image[20];
   float hilbert[64];
   float sine[260];
+  float pk_consts[8];      /* {1,1,-1,-1,-0,-0}: multiplicands / addends of the packed FMA forms, deliberately run-time data (sdr_pipeline.cuh, PkConst) */
 } SdrTables;
 
 typedef struct {
