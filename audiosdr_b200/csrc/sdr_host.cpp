@@ -410,6 +410,15 @@ int fold_profile(sdr_batch *h) {
     h->prof_load[cls * (SDR_STAGES + 1) + SDR_STAGES] += rows[(size_t)g * SDR_PROF_SLOTS + 15];
     for (int e = 0; e < 16; e++) h->prof_crit[cls * 16 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 40 + e];
     for (int e = 0; e < SDR_STAGES; e++) h->prof_bar[cls * SDR_STAGES + e] += rows[(size_t)g * SDR_PROF_SLOTS + 64 + e];
+    if (g == 5 && getenv("SDR_ROLE_PROFILE_NB")) /* time line of one CTA: steps 200..203 of the last profiled launch */
+      for (int st = 0; st < 4; st++) {
+        fprintf(stderr, "[sdr] time line, step %d (cycles after the previous release: start, end, arrival, release):", 200 + st);
+        for (int w = 0; w < SDR_STAGES; w++) {
+          const unsigned long long *tl = &rows[(size_t)g * SDR_PROF_SLOTS + 128 + (st * SDR_STAGES + w) * 4];
+          fprintf(stderr, " [%d: %llu %llu %llu %llu]", w, tl[0], tl[1], tl[2], tl[3]);
+        }
+        fprintf(stderr, "\n");
+      }
     h->prof_groups[cls] += h->prof_launches;
   }
   if (dev_zero(h->d_prof, rows.size() * 8, h->last_stream)) return SDR_ERR_CUDA;

@@ -30,19 +30,28 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n
   const uint32_t steps = n_tiles + (uint32_t)dmax;
   long long busy = 0, at_barrier = 0, t_begin = prof ? clock64() : 0;
   uint16_t *scr = reinterpret_cast<uint16_t *>(x.smem + S_PROFSCR);
+  long long t_rel = t_begin; /* release of the previous step barrier, as this warp saw it */
 #pragma unroll 1
   for (uint32_t s = 0; s < steps; s++) {
     const long long tau = (long long)s - delay;
-    long long b = 0;
+    long long b = 0, t0 = 0, t1 = 0;
     if (tau >= 0 && tau < (long long)n_tiles && !(prof && ((x.L->diag_skip >> role) & 1u))) {
-      const long long t0 = prof ? clock64() : 0;
+      t0 = prof ? clock64() : 0;
       body((uint32_t)tau);
-      if (prof) { b = clock64() - t0; busy += b; }
+      if (prof) { t1 = clock64(); b = t1 - t0; busy += b; }
     }
     if (prof && (threadIdx.x & 31) == 0) scr[(s & 1) * 16 + role] = (uint16_t)(b >> 4);
     const long long tb = prof ? clock64() : 0;
     step_barrier();
-    if (prof) at_barrier += clock64() - tb;
+    if (prof) {
+      const long long te = clock64();
+      at_barrier += te - tb;
+      if (s >= 200 && s < 204 && (threadIdx.x & 31) == 0) { /* time line: body start, body end, barrier arrival, release; relative to the previous release */
+        unsigned long long *tl = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS + 128 + ((s - 200) * SDR_STAGES + role) * 4;
+        tl[0] = (unsigned long long)(t0 - t_rel); tl[1] = (unsigned long long)(t1 - t_rel); tl[2] = (unsigned long long)(tb - t_rel); tl[3] = (unsigned long long)(te - t_rel);
+      }
+      t_rel = te;
+    }
     if (prof && role == 0 && (threadIdx.x & 31) == 0) { /* which stage did this step wait for? */
       uint32_t mx = 0; int arg = 0;
       for (int w = 0; w < SDR_STAGES; w++) { const uint32_t v = (uint32_t)scr[(s & 1) * 16 + w] << 4; if (v > mx) { mx = v; arg = w; } }

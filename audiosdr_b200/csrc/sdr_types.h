@@ -122,7 +122,7 @@ typedef struct {
 #define SDR_MAP_ENV_DEFAULT 0xA0D459B1328C67ull
 
 #define SDR_STAGES 14     /* pipeline stages = warps per CTA */
-#define SDR_PROF_SLOTS 96
+#define SDR_PROF_SLOTS 512 /* [0..95] counters, [128..] a time line of four steps of every stage (diagnostics twin only) */
 
 #define SDR_AGC_LUT_STRIDE 132
 

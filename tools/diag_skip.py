@@ -50,13 +50,18 @@ def run(keep, label, extra=0):
 
 
 ALL = list(range(14))
-os.environ["SDR_ROLE_PROFILE_NB"] = "1"
+os.environ.pop("SDR_ROLE_PROFILE_NB", None)
 run(ALL, "all stages")
-run([0], "IN only")
-run([0], "IN only, no input requests", 0x10000)
-run([0], "IN only, no blanker-ring stores", 0x20000)
-run([0], "IN only, neither", 0x30000)
-run([12], "ENVL only")
-run([13], "NB-out only")
 run([5], "one Hilbert only")
-run(ALL, "all stages (again)")
+run([5, 6], "Hil+Hil same sub-partition (default map: warps 8, 4)")
+run([5, 7], "Hil+Hil different sub-partitions")
+run([5, 6, 7, 8], "Hilbert x4 (2+2)")
+os.environ["SDR_MAP_SSB"] = "32A90D41CB8765"   # one Hilbert + one cascade per sub-partition
+run(ALL, "balanced map: all stages")
+run([5, 6, 7, 8], "balanced map: Hilbert x4 (1+1+1+1)")
+run([5, 2], "balanced map: Hil + IF-I same sub-partition")
+run([2], "balanced map: IF-I only")
+run([2, 3, 9], "balanced map: cascades x3 (1+1+1)")
+run([5, 6, 7, 8, 2, 3, 9], "balanced map: Hilbert x4 + cascades x3")
+run([5, 6, 7, 8, 2, 3, 9, 4, 10], "balanced map: + NCO + AGC")
+run([w for w in ALL if w not in (1, 12, 13)], "balanced map: all but blanker stages")
