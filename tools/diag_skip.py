@@ -53,15 +53,16 @@ ALL = list(range(14))
 os.environ.pop("SDR_ROLE_PROFILE_NB", None)
 run(ALL, "all stages")
 run([5], "one Hilbert only")
-run([5, 6], "Hil+Hil same sub-partition (default map: warps 8, 4)")
-run([5, 7], "Hil+Hil different sub-partitions")
-run([5, 6, 7, 8], "Hilbert x4 (2+2)")
+run([5, 6], "Hil+Hil same sub-partition")
+run([2], "IF-I only")
+run([2, 3], "IF-I + IF-Q same sub-partition")
+run([2, 3, 9], "three cascades same sub-partition")
+run([2, 3, 9, 12], "sub-partition 1 as placed: 3 cascades + ENVL")
+run([0, 5, 6, 11], "sub-partition 0 as placed: IN Hil Hil OUT")
+run([7, 8, 13], "sub-partition 2 as placed: Hil Hil NB-out")
+run([1, 4, 10], "sub-partition 3 as placed: NB-scan NCO AGC")
 os.environ["SDR_MAP_SSB"] = "32A90D41CB8765"   # one Hilbert + one cascade per sub-partition
-run(ALL, "balanced map: all stages")
-run([5, 6, 7, 8], "balanced map: Hilbert x4 (1+1+1+1)")
 run([5, 2], "balanced map: Hil + IF-I same sub-partition")
-run([2], "balanced map: IF-I only")
-run([2, 3, 9], "balanced map: cascades x3 (1+1+1)")
+run([5, 2, 13, 11], "balanced map: Hil + IF-I + NB-out + OUT (one sub-partition)")
 run([5, 6, 7, 8, 2, 3, 9], "balanced map: Hilbert x4 + cascades x3")
-run([5, 6, 7, 8, 2, 3, 9, 4, 10], "balanced map: + NCO + AGC")
-run([w for w in ALL if w not in (1, 12, 13)], "balanced map: all but blanker stages")
+run(ALL, "balanced map: all stages")
