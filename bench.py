@@ -67,14 +67,42 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region is a few tens of
+    milliseconds, so the samples come from NVML polled by a thread every ~2 ms; nvidia-smi (one sample per 100 ms at
+    best) is the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.p = index, [], None
+        self.index, self.rows, self.p, self.t, self.stop_flag = index, [], None, None, False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))); self.mx.append(mx)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True); self.t.start()
+            return
+        except Exception:
+            self.t = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                        "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -87,6 +115,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.t is not None:
+            self.stop_flag = True; self.t.join(timeout=1.0)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml"}
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)), "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml, polled every 2 ms inside the timed region"}
         if self.p:
             self.p.terminate()
         sm, mx, reasons = [], [], set()
@@ -99,8 +133,8 @@ class ClockSampler:
             except Exception:
                 pass
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvidia-smi"}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def synth_planes(dev, first_channel, n_channels, n_samples, seed, config_id=CONFIG_ID):
