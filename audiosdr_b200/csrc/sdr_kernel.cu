@@ -347,6 +347,37 @@ __global__ void sdr_selftest_envelope_kernel(unsigned first, unsigned step, unsi
   if (local) atomicAdd(bad, local);
 }
 
+/* ---- self-test: div_inrange (the PLL's division without range check and slow-path branch) against the IEEE divide, bit for
+ * bit, over `n` pseudo-random operand pairs of both signs whose magnitudes cover [2^-60, 2^60] exponent by exponent
+ * (mantissas from a 64-bit mix of the pair index; every 16th pair sits on a power of two or one ulp beside it). */
+__global__ void sdr_selftest_divide_kernel(unsigned long long seed, unsigned long long n, unsigned long long *bad) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long local = 0;
+  for (; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned long long z = seed + i * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    unsigned ma = (unsigned)z & 0x7FFFFFu, mb = (unsigned)(z >> 23) & 0x7FFFFFu;
+    const unsigned ea = 67u + (unsigned)((z >> 46) % 121u), eb = 67u + (unsigned)((z >> 54) % 121u); /* 2^-60 .. 2^60 */
+    if ((i & 15ull) == 0) { ma = (z >> 62) & 1 ? 0u : 0x7FFFFFu; mb = (z >> 63) ? 0u : 1u; }
+    if (ea == 187u) ma = 0; /* 2^60 itself is the upper end */
+    if (eb == 187u) mb = 0;
+    const float a = __uint_as_float(((unsigned)(i & 1) << 31) | (ea << 23) | ma);
+    const float b = __uint_as_float(((unsigned)((i >> 1) & 1) << 31) | (eb << 23) | mb);
+    if (__float_as_uint(div_inrange(a, b)) != __float_as_uint(__fdiv_rn(a, b))) local++;
+  }
+  if (local) atomicAdd(bad, local);
+}
+
+extern "C" int sdrk_selftest_divide(unsigned long long seed, unsigned long long n, unsigned long long *mismatches) {
+  unsigned long long *d = nullptr;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return 1;
+  cudaMemset(d, 0, 8);
+  sdr_selftest_divide_kernel<<<148 * 8, 256>>>(seed, n, d);
+  cudaError_t e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : 2;
+}
+
 extern "C" int sdrk_selftest_envelope(unsigned first, unsigned step, unsigned long long n, unsigned long long *mismatches) {
   unsigned long long *d = nullptr;
   if (cudaMalloc(&d, 8) != cudaSuccess) return 1;

@@ -182,6 +182,17 @@ def test_cuda_batched_envelope_equals_ieee_divide(cuda_lib):
         assert bad.value == 0, (hex(first), step, n, bad.value)
 
 
+def test_cuda_inrange_divide_equals_ieee_divide(cuda_lib):
+    """div_inrange (the SAM PLL's division: fast path without range check / slow-path branch) == IEEE divide for 2^30
+    operand pairs covering every exponent pair of [2^-60, 2^60], both signs, powers of two and their neighbours."""
+    import ctypes as C
+    cuda_lib.sdrk_selftest_divide.argtypes = [C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+    for seed in (1, 0xD1B54A32D192ED03):
+        bad = C.c_ulonglong(12345)
+        assert cuda_lib.sdrk_selftest_divide(seed, 1 << 29, C.byref(bad)) == 0
+        assert bad.value == 0, (seed, bad.value)
+
+
 def test_cuda_ragged_shapes_and_pitches(cuda_lib, oracle, dev):
     """Edge cases: 1 and 33 channels (partly filled groups), one block per call, row pitch larger than the call,
     planes that are views into a bigger buffer, int16 in / float32 out and the reverse."""
