@@ -24,6 +24,7 @@ int main() {
         int want = (int)((uint16_t)(long)((double)ph * 65535.0 / (double)two_pi));
         int got = sdrk::lut_index(ph);
         if (ph < two_pi && want != got) { if (b < 5) fprintf(stderr, "mismatch at %a: want %d got %d\n", ph, want, got); b++; }
+        if (sdrk::lut_index_lt8(ph) != got) { if (b < 5) fprintf(stderr, "lut_index_lt8 mismatch at %a\n", ph); b++; } /* the PLL's clamp-free form, all of [0, 8) */
       }
       bad += b;
     });
@@ -73,7 +74,11 @@ int main() {
           for (uint64_t u = (uint64_t)(top + 1) * t / nt; u < (uint64_t)(top + 1) * (t + 1) / nt; u++) {
             uint32_t bits = (uint32_t)u | (sign ? 0x80000000u : 0u); float x; memcpy(&x, &bits, 4);
             float want, got;
-            if (which == 0) { want = (float)((double)x + SDR_PI_D / 2.0); got = sdrk::add_half_pi(x); }
+            if (which == 0) {
+              want = (float)((double)x + SDR_PI_D / 2.0); got = sdrk::add_half_pi(x);
+              const float got2 = sdrk::add_half_pi_inrange(x); /* the PLL's Fast2Sum form */
+              if (memcmp(&want, &got2, 4)) { if (b < 5) fprintf(stderr, "add_half_pi_inrange mismatch at %a\n", x); b++; }
+            }
             else if (which == 1) { want = (float)((double)x + SDR_PI_D); got = sdrk::add_pi(x); }
             else { want = (float)((double)x - SDR_PI_D); got = sdrk::sub_pi(x); }
             if (memcmp(&want, &got, 4)) { if (b < 5) fprintf(stderr, "add_dconst(%d) mismatch at %a\n", which, x); b++; }
