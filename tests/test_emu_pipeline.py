@@ -54,6 +54,31 @@ def test_emulated_setter_fuzz(oracle, emu_lib):
     assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
 
 
+ALS_EDGE_PARAMS = [(126, 0.5, 3), (125, 0.3, 0), (128, 0.25, 1), (124, 0.5, 5), (1, 0.5, 0), (4, 0.6, 1), (55, 0.5, 3), (97, 0.1, 19), (60, 0.5, 69)]
+
+
+def als_edge_events(nch):
+    """ALS tap counts / delays at the ends of their ranges (C:393-398): taps up to the last array slot, no delay at all
+    (the one case where a tile cannot pre-compute its successor's first sum), a history reaching the far end of the ring."""
+    ev = []
+    for c in range(nch):
+        m, lam, d = ALS_EDGE_PARAMS[c % len(ALS_EDGE_PARAMS)]
+        ev += [(c, 0, "setALSfilterParams", m, lam, d), (c, 0, "enableALSfilter"), (c, 0, "setALSfilterAdaptive" if c % 4 else "setALSfilterStatic")]
+        ev += [(c, 0, "setALSfilterNotch" if c % 2 else "setALSfilterPeak")]
+        if c % 3 == 0:
+            ev += [(c, 7, "setALSfilterParams", ALS_EDGE_PARAMS[(c + 1) % len(ALS_EDGE_PARAMS)][0], 0.4, c % 2)]
+    return ev
+
+
+def test_emulated_als_edge_parameters(oracle, emu_lib):
+    nch = 2 * len(ALS_EDGE_PARAMS)
+    I, Q, ev = S.make(4, list(range(nch)), 14)
+    ev = [e for e in ev if not e[2].startswith("setALSfilterParams")] + als_edge_events(nch)
+    o = oracle.run(I, Q, ev, threads=4)
+    a = harness.run_batch(emu_lib, I, Q, ev, chunks=(3, 1, 6, 4))
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+
+
 def test_argument_errors(emu_lib):
     import audiosdr_b200 as A
     b = A.SdrBatch(3, _lib=emu_lib)

@@ -182,6 +182,19 @@ def test_cuda_batched_envelope_equals_ieee_divide(cuda_lib):
         assert bad.value == 0, (hex(first), step, n, bad.value)
 
 
+def test_cuda_als_edge_parameters(cuda_lib, oracle, dev):
+    """ALS tap counts / delays at the ends of their ranges (taps up to the last array slot, delay 0 -- the one case where
+    a tile cannot pre-compute its successor's first FIR sum --, histories reaching the far end of the ring), parameters
+    changed mid-stream, calls of 1 to 40 blocks."""
+    from test_emu_pipeline import ALS_EDGE_PARAMS, als_edge_events
+    nch = 4 * len(ALS_EDGE_PARAMS) + 3
+    I, Q, ev = S.make(4, list(range(nch)), 60)
+    ev = [e for e in ev if not e[2].startswith("setALSfilterParams")] + als_edge_events(nch)
+    o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
+    a = harness.run_batch(cuda_lib, I, Q, ev, chunks=(3, 1, 40, 2), device=dev)
+    assert_same(a, o["audio"])
+
+
 def test_cuda_inrange_divide_equals_ieee_divide(cuda_lib):
     """div_inrange (the SAM PLL's division: fast path without range check / slow-path branch) == IEEE divide for 2^30
     operand pairs covering every exponent pair of [2^-60, 2^60], both signs, powers of two and their neighbours."""
