@@ -211,9 +211,16 @@ def cpu_reference_rate(seconds, cores):
 WORKLOAD = "BASELINE configs[1]: 4096 channels/GPU, mixed CW_LSB/CW_USB/LSB/USB, NB(10 dB)+AGC(medium)+audio BPF"
 
 
-def config_dict(nch, nblk):
+DIAG_WORKLOADS = {3: "DIAGNOSTIC (not the headline): BASELINE configs[2], SAM channels with carrier PLL + AGC, +-50 Hz offsets",
+                  5: "DIAGNOSTIC (not the headline): BASELINE configs[4], WSPR-mode channels"}
+
+
+def config_dict(nch, nblk, cfg_id=None, variant=None):
     ns = nblk * 128
-    return dict(workload=WORKLOAD, channels_per_gpu=nch, blocks_per_step=nblk, samples_per_step=int(nch) * ns,
+    wl = WORKLOAD if cfg_id in (None, CONFIG_ID) else "%s, %d channels/GPU" % (DIAG_WORKLOADS[cfg_id], nch)
+    if variant:
+        wl = "DIAGNOSTIC (not the headline): " + wl + " with switches [%s]" % variant
+    return dict(workload=wl, channels_per_gpu=nch, blocks_per_step=nblk, samples_per_step=int(nch) * ns,
                 planes="float32 channel-major in HBM",
                 l2="inputs per step %.0f MB >> 126 MB L2, no flush needed" % (2 * nch * ns * 4 / 1e6),
                 parallelism="channels sharded, no collective")
@@ -420,7 +427,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=cnt["max_ms"] / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                     data="synthetic",
-                    config=config_dict(nch, nblk),
+                    config=config_dict(nch, nblk, cfg_id, args.variant or None),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_fp32=fp32, cpu_baseline=cpu,
                     role_profile=role_profile, variant=args.variant or None,
                     diagnostic_workload=(None if cfg_id == CONFIG_ID else "BASELINE configs[%d], %d channels/GPU: NOT the headline metric" % (cfg_id - 1, nch)),

@@ -20,13 +20,23 @@ try:
 except Exception as e: print('role profile failed', e)
 PY
 for w in 3 5; do
-  echo "== diagnostic workload $w"; timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --role-profile > gpurun_out/${TAG}_diag_w$w.json 2> gpurun_out/${TAG}_diag_w$w.err
+  echo "== diagnostic workload $w (product kernel, then the profiling twin with per-stage busy fractions)"
+  timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${TAG}_diag_w$w.json 2> gpurun_out/${TAG}_diag_w$w.err
+  timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --role-profile > gpurun_out/${TAG}_diag_w${w}_roles.json 2>> gpurun_out/${TAG}_diag_w$w.err
   python -c "
 import json
 try:
-    d=json.loads(open('gpurun_out/${TAG}_diag_w$w.json').read().strip().splitlines()[-1]); print('workload $w:', round(d['value']), 'Msps', d['parity'], {k:{kk:round(vv,3) for kk,vv in v.items()} for k,v in (d['role_profile'] or {}).items()})
+    d=json.loads(open('gpurun_out/${TAG}_diag_w$w.json').read().strip().splitlines()[-1]); r=json.loads(open('gpurun_out/${TAG}_diag_w${w}_roles.json').read().strip().splitlines()[-1])
+    print('workload $w:', round(d['value']), 'Msps', d['parity'], '| twin', round(r['value']), {k:{kk:round(vv,3) for kk,vv in v.items()} for k,v in (r['role_profile'] or {}).items()})
 except Exception as e: print('diag failed', e); print(open('gpurun_out/${TAG}_diag_w$w.err').read()[-500:])"
 done
+echo "== diagnostic: headline workload with the ALS filter on every channel"
+timeout 600 python bench.py --variant als --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${TAG}_diag_als.json 2> gpurun_out/${TAG}_diag_als.err
+python -c "
+import json
+try:
+    d=json.loads(open('gpurun_out/${TAG}_diag_als.json').read().strip().splitlines()[-1]); print('als variant:', round(d['value']), 'Msps')
+except Exception as e: print('als diag failed', e)"
 echo "== compute-sanitizer (all-mode smoke case)"
 for t in memcheck racecheck synccheck initcheck; do
   timeout 420 compute-sanitizer --tool $t --kernel-name kernel_substring=sdr_ --print-limit 3 python tools/sanitize_smoke.py > gpurun_out/${TAG}_sanitize_$t.log 2>&1
