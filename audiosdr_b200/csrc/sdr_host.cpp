@@ -601,8 +601,10 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
   if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
   /* chunking along time: ~12 chunks per call, at least 16 blocks each (every chunk is one kernel launch that
    * reloads and saves the per-channel state, so chunks should not be tiny) */
-  uint32_t chunk = (n_blocks + 11) / 12;
-  if (chunk < 16) chunk = 16;
+  static const uint32_t want_chunks = []() { const char *e = getenv("SDR_HOST_CHUNKS"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 12); }();
+  static const uint32_t min_chunk = []() { const char *e = getenv("SDR_HOST_MIN_CHUNK"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 16); }();
+  uint32_t chunk = (n_blocks + want_chunks - 1) / want_chunks;
+  if (chunk < min_chunk) chunk = min_chunk;
   if (chunk > n_blocks) chunk = n_blocks;
   if (h->desc.max_blocks_per_call && chunk > h->desc.max_blocks_per_call) chunk = h->desc.max_blocks_per_call;
   const size_t cs = (size_t)chunk * SDR_BLOCK_SAMPLES;
