@@ -78,6 +78,8 @@ int main() {
               want = (float)((double)x + SDR_PI_D / 2.0); got = sdrk::add_half_pi(x);
               const float got2 = sdrk::add_half_pi_inrange(x); /* the PLL's Fast2Sum form */
               if (memcmp(&want, &got2, 4)) { if (b < 5) fprintf(stderr, "add_half_pi_inrange mismatch at %a\n", x); b++; }
+              if ((got2 < 0.0f) != (x < -0x1.921fb4p+0f)) { if (b < 5) fprintf(stderr, "cosine wrap compare mismatch at %a\n", x); b++; }
+              if (x >= -0x1.921fb6p+1f && x <= 0x1.921fb6p+1f && sdrk::lut_index_cos(x) != sdrk::lut_index_below_2pi(got2)) { if (b < 5) fprintf(stderr, "lut_index_cos mismatch at %a\n", x); b++; }
             }
             else if (which == 1) { want = (float)((double)x + SDR_PI_D); got = sdrk::add_pi(x); }
             else { want = (float)((double)x - SDR_PI_D); got = sdrk::sub_pi(x); }
