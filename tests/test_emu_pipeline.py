@@ -54,6 +54,26 @@ def test_emulated_setter_fuzz(oracle, emu_lib):
     assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
 
 
+def test_emulated_pll_general_path_alone(oracle, monkeypatch):
+    """The SAM PLL evaluates the tracking case as straight-line code behind a warp vote and everything else through the
+    reference's general control flow; both must give the oracle's bits.  The default run takes whichever applies per
+    sample; here every vote is made to fail, so the general path computes every sample (a fresh library instance: the
+    switch is read once)."""
+    import ctypes, shutil, subprocess, tempfile
+    from audiosdr_b200 import api
+    monkeypatch.setenv("SDR_EMU_VOTE_FAILS", "1")
+    emu_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+    subprocess.run(["make", "-s", "-C", emu_dir], check=True)
+    with tempfile.TemporaryDirectory() as d:
+        dst = os.path.join(d, "libsdr_emu_general.so")  # a copy under another name is a separate instance for the loader
+        shutil.copy(os.path.join(emu_dir, "libsdr_emu.so"), dst)
+        lib = api._bind(ctypes.CDLL(dst))
+        I, Q, ev = S.make(3, list(range(8)), 30)
+        o = oracle.run(I, Q, ev, threads=4)
+        a = harness.run_batch(lib, I, Q, ev, chunks=(7, 23))
+        assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+
+
 ALS_EDGE_PARAMS = [(126, 0.5, 3), (125, 0.3, 0), (128, 0.25, 1), (124, 0.5, 5), (1, 0.5, 0), (4, 0.6, 1), (55, 0.5, 3), (97, 0.1, 19), (60, 0.5, 69)]
 
 
