@@ -231,7 +231,7 @@ int apply_one(sdr_batch *h, uint32_t c, uint32_t op, float a0, float a1, float a
       s.in_gain = g; s.in_gain_i = s.in_gain * s.gain_balance; s.in_gain_q = s.in_gain; } break;
     case SDR_SET_setIQgainBalance: { float bal = sqrtf(a0); /* a LOCAL in the reference: the member stays 1 (Q7) */
       s.in_gain_i = s.in_gain * bal; s.in_gain_q = s.in_gain / bal; } break;
-    case SDR_SET_setDemodMode: return set_mode(h, c, (int)a0);
+    case SDR_SET_setDemodMode: { int rc = set_mode(h, c, (int)a0); if (rc) return rc; } break; /* falls through to cfg_dirty: mode, phase increment and IF set are device configuration */
     case SDR_SET_enableAudioFilter: s.aud_on = true; break;
     case SDR_SET_disableAudioFilter: s.aud_on = false; break;
     case SDR_SET_setOutputGain: s.out_gain = a0; break;

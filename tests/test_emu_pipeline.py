@@ -125,3 +125,22 @@ def test_channel_results_do_not_depend_on_batch_position(oracle, emu_lib):
         sub_ev += [(new,) + tuple(e[1:]) for e in ev if e[0] == old]
     sub = harness.run_batch(emu_lib, I[perm], Q[perm], sub_ev, chunks=(5, 7))
     assert harness.bits_equal(sub, full[perm])
+
+
+def lone_mode_switch_case():
+    """A setDemodMode that is the ONLY setter at its block boundary (regression: it used to skip the device
+    configuration upload): same-class switches (LSB->USB, USB->CW_USB, AM->SAM) and class changes (SSB<->AM/SAM)."""
+    I, Q, ev = S.make(4, list(range(14)), 30)
+    ev = [e for e in ev if e[1] == 0]
+    switches = [(0, 5, 1), (1, 5, 3), (2, 6, 4), (3, 6, 0), (4, 7, 5), (5, 7, 6), (6, 8, 2), (7, 9, 5), (8, 9, 4), (9, 11, 1),
+                (0, 13, 4), (2, 14, 5), (2, 17, 1), (10, 19, 6), (11, 21, 0), (12, 23, 4), (13, 25, 3)]
+    ev += [(c, blk, "setDemodMode", m) for c, blk, m in switches]
+    return I, Q, ev
+
+
+def test_emulated_lone_mode_switch(oracle, emu_lib):
+    I, Q, ev = lone_mode_switch_case()
+    o = oracle.run(I, Q, ev, threads=4)
+    a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(30,), return_batch=True)
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)

@@ -94,6 +94,16 @@ def test_cuda_float32_planes_and_gains(cuda_lib, oracle, dev):
     assert_same(ai, oi["audio"])
 
 
+def test_cuda_lone_mode_switch(cuda_lib, oracle, dev):
+    """setDemodMode as the only setter at a block boundary (same-class and SSB<->AM/SAM class changes)."""
+    from test_emu_pipeline import lone_mode_switch_case
+    I, Q, ev = lone_mode_switch_case()
+    o = oracle.run(I, Q, ev, threads=4)
+    a, b = harness.run_batch(cuda_lib, I, Q, ev, chunks=(30,), device=dev, return_batch=True)
+    assert_same(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+
+
 def test_cuda_setter_fuzz(cuda_lib, oracle, dev):
     rng = np.random.default_rng(4321)
     I, Q, ev = S.make(4, list(range(64)), 48)
