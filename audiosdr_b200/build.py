@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdr_batch.so")
 SOURCES = ["sdr_kernel.cu", "sdr_host.cpp"]
-DEPS = SOURCES + ["sdr_pipeline.cuh", "sdr_types.h", "sdr_kernel.h", "sdr_tables.inc", os.path.join("..", "..", "include", "sdr_batch.h")]
+DEPS = SOURCES + ["sdr_pipeline.cuh", "sdr_lay.h", "sdr_types.h", "sdr_kernel.h", "sdr_tables.inc", os.path.join("..", "..", "include", "sdr_batch.h")]
 
 # -fmad=false: the reference rounds every product and every sum separately (x86-64 SSE, no FMA); contraction
 # would change low bits and, through the blanker/AGC/PLL thresholds, whole decisions.  Division and square root

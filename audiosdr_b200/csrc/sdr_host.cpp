@@ -25,6 +25,7 @@
 
 #include "../../include/sdr_batch.h"
 #include "sdr_kernel.h"
+#include "sdr_lay.h"
 #include "sdr_tables.inc"
 #include "sdr_types.h"
 
@@ -133,8 +134,13 @@ void build_agc_lut(float thr, float slope, float knee, float *lut) {
 
 }  // namespace
 
+/* the groups of one pipeline class with one set of optional stages: one kernel launch with its own shared-memory plan */
+struct Bucket { SdrLay lay; uint32_t first, count; };
+
 struct sdr_batch {
   sdr_batch_desc desc;
+  std::vector<Bucket> buckets;
+  void *s_aux[8]; void *ev_fork, *ev_join[8]; /* buckets beyond the first run on their own streams, forked from / joined to the caller's */
   uint32_t n_ch; size_t ch_stride;
   std::vector<Shadow> sh;
   std::vector<uint32_t> pend_reset; /* per channel SDRK_R_* bits to replay before the next block */
@@ -292,33 +298,74 @@ void resolve(const Shadow &s, SdrChanCfg &c) {
   c.nb_thr = s.nb_thr; c.als_m = s.als_m; c.als_delay = s.als_delay; c.als_lambda = s.als_lambda;
 }
 
-void build_groups(sdr_batch *h) {
-  h->h_groups.clear();
-  /* Channels of one class share groups; inside a class they are ordered by mode so that the lanes of a warp
-   * mostly run the same oscillator frequency and coefficient set (channel results never depend on the grouping). */
+uint32_t lay_feat_of(uint32_t flags) { return ((flags & CF_NB) ? LF_NB : 0u) | ((flags & CF_ALS) ? LF_ALS : 0u); }
+
+int env_int(const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; }
+
+/* Tile length and shared-memory budget of a bucket.  A group's time does not depend on how many other groups run, so
+ * when a launch has more groups than SMs the plan trades ring slack for co-residency: shorter tiles shrink every ring
+ * that is sized in tiles.  (SDR_TILE_SSB / SDR_TILE_ENV / SDR_CTAS_PER_SM / SDR_SLACK override the choice for experiments.) */
+int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
+  (void)n_sm;
+  int T = 32, ctas = 1;
+  const int t_env = env_int(cls == CLS_SSB ? "SDR_TILE_SSB" : "SDR_TILE_ENV", 0);
+  if (t_env && !(feat & (LF_NB | LF_ALS))) T = t_env;
+  const int c_env = env_int("SDR_CTAS_PER_SM", 0);
+  if (c_env > 0) ctas = c_env;
+  const int slack = env_int("SDR_SLACK", 2);
+  const int budget = (233472 - 1024 * ctas) / ctas; /* an SM has 228 KB, each resident CTA costs 1 KB of it */
+  int rc = lay_build(&b.lay, cls, feat, T, budget > 232448 ? 232448 : budget, slack);
+  if (rc) rc = lay_build(&b.lay, cls, feat, 32, 232448, 0);
+  if (rc) return rc;
+  /* measured placements exist for the launches that run all 14 stages */
+  if (b.lay.n_warps == SDR_STAGES) {
+    unsigned long long m = cls == CLS_SSB ? SDR_MAP_SSB_DEFAULT : SDR_MAP_ENV_DEFAULT;
+    if (const char *e = getenv(cls == CLS_SSB ? "SDR_MAP_SSB" : "SDR_MAP_ENV")) m = strtoull(e, nullptr, 16);
+    lay_place(&b.lay, m);
+  } else if (const char *e = getenv(cls == CLS_SSB ? "SDR_MAP_SSB_LEAN" : "SDR_MAP_ENV_LEAN")) lay_place(&b.lay, strtoull(e, nullptr, 16));
+  return 0;
+}
+
+int build_groups(sdr_batch *h) {
+  h->h_groups.clear(); h->buckets.clear();
+  /* Channels of one class with the same optional stages share groups (= one bucket, one launch); inside a bucket they are
+   * ordered by mode so that the lanes of a warp run the same oscillator frequency and coefficient set (channel results
+   * never depend on the grouping). */
   static const int order[2][5] = {{SDR_LSB, SDR_USB, SDR_CW_LSB, SDR_CW_USB, SDR_WSPR}, {SDR_AM, SDR_SAM, -1, -1, -1}};
+  std::vector<uint32_t> by_key[2][4][5];
+  for (uint32_t c = 0; c < h->n_ch; c++) {
+    const int m = h->sh[c].mode, cls = (m == SDR_AM || m == SDR_SAM) ? CLS_ENV : CLS_SSB;
+    int mi = 0;
+    for (int k = 0; k < 5; k++) if (order[cls][k] == m) mi = k;
+    by_key[cls][lay_feat_of(h->h_cfg[c].flags)][mi].push_back(c);
+  }
   for (int cls = 0; cls < 2; cls++) {
-    SdrGroup g; int fill = 0;
-    auto flush = [&]() {
-      if (!fill) return;
-      for (int l = fill; l < SDR_LANES; l++) g.cid[l] = -1;
-      h->h_groups.push_back(g); fill = 0;
-    };
-    for (int mi = 0; mi < 5; mi++) {
-      if (order[cls][mi] < 0) continue;
-      for (uint32_t c = 0; c < h->n_ch; c++) {
-        if (h->sh[c].mode != order[cls][mi]) continue;
-        if (!fill) { memset(&g, 0, sizeof g); g.cls = cls; }
-        g.cid[fill++] = (int32_t)c;
-        if (fill == SDR_LANES) flush();
+    for (uint32_t feat = 0; feat < 4; feat++) {
+      Bucket b; b.first = (uint32_t)h->h_groups.size();
+      SdrGroup g; int fill = 0;
+      auto flush = [&]() {
+        if (!fill) return;
+        for (int l = fill; l < SDR_LANES; l++) g.cid[l] = -1;
+        h->h_groups.push_back(g); fill = 0;
+      };
+      for (int mi = 0; mi < 5; mi++) {
+        for (uint32_t c : by_key[cls][feat][mi]) {
+          if (!fill) { memset(&g, 0, sizeof g); g.cls = cls; }
+          g.cid[fill++] = (int32_t)c;
+          if (fill == SDR_LANES) flush();
+        }
+        /* SSB class: a group never mixes modes, so that all its lanes share one oscillator (RoleNco's table path) */
+        if (cls == CLS_SSB) flush();
       }
-      /* SSB class: a group never mixes modes, so that all its lanes share one oscillator (RoleNco's table path);
-       * at most 4 partly filled groups per handle */
-      if (cls == CLS_SSB) flush();
+      flush();
+      b.count = (uint32_t)h->h_groups.size() - b.first;
+      if (!b.count) continue;
+      if (plan_bucket(b, cls, feat, 148)) return fail(SDR_ERR_UNSUPPORTED, "no shared-memory plan for a bucket (internal)");
+      h->buckets.push_back(b);
     }
-    flush();
   }
   h->n_groups = (uint32_t)h->h_groups.size();
+  return 0;
 }
 
 int fold_profile(sdr_batch *h);
@@ -343,7 +390,7 @@ int sync_config(sdr_batch *h, void *stream) {
   }
   if (h->groups_dirty) {
     if (h->prof_on && fold_profile(h)) return SDR_ERR_CUDA; /* rows are per group: fold before the grouping changes */
-    build_groups(h);
+    { int rc = build_groups(h); if (rc) return rc; }
     for (SdrGroup &g : h->h_groups) {
       g.feat = 0;
       for (int k = 0; k < SDR_LUT_SLOTS; k++) g.lut_ids[k] = -1;
@@ -400,25 +447,13 @@ int fold_profile(sdr_batch *h) {
   if (d2h(rows.data(), h->d_prof, rows.size() * 8, h->last_stream) || dev_sync(h->last_stream)) return SDR_ERR_CUDA;
   for (uint32_t g = 0; g < h->n_groups && g < h->h_groups.size(); g++) {
     int cls = h->h_groups[g].cls;
-    /* row layout (sdr_kernel.cu pipeline_loop, Probe::flush): [0..13] busy per stage, [14] CTA pipeline cycles, [15] prologue,
-     * [16..29] state-load cycles per stage, [30..32] NB sub-phases, [33..35] IN sub-phases, [40..53] steps in which the stage was
-     * the last to finish, [54] sum over steps of the slowest stage's busy cycles, [55] steps */
+    /* row layout (sdr_kernel.cu pipeline_loop, Probe::flush): [0..13] busy cycles per stage, [14] CTA pipeline cycles, [15] prologue,
+     * [16..29] cycles per stage spent waiting for other stages, [30..32] NB sub-phases, [33..35] IN sub-phases */
     for (int w = 0; w < SDR_STAGES; w++) h->prof_busy[cls * SDR_STAGES + w] += rows[(size_t)g * SDR_PROF_SLOTS + w];
     h->prof_total[cls] += rows[(size_t)g * SDR_PROF_SLOTS + 14];
     for (int e = 0; e < 6; e++) h->prof_extra[cls * 8 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 30 + e];
-    for (int e = 0; e < SDR_STAGES; e++) h->prof_load[cls * (SDR_STAGES + 1) + e] += rows[(size_t)g * SDR_PROF_SLOTS + 16 + e];
     h->prof_load[cls * (SDR_STAGES + 1) + SDR_STAGES] += rows[(size_t)g * SDR_PROF_SLOTS + 15];
-    for (int e = 0; e < 16; e++) h->prof_crit[cls * 16 + e] += rows[(size_t)g * SDR_PROF_SLOTS + 40 + e];
-    for (int e = 0; e < SDR_STAGES; e++) h->prof_bar[cls * SDR_STAGES + e] += rows[(size_t)g * SDR_PROF_SLOTS + 64 + e];
-    if (g == 5 && getenv("SDR_ROLE_PROFILE_NB")) /* time line of one CTA: steps 200..203 of the last profiled launch */
-      for (int st = 0; st < 4; st++) {
-        fprintf(stderr, "[sdr] time line, step %d (cycles after the previous release: start, end, arrival, release):", 200 + st);
-        for (int w = 0; w < SDR_STAGES; w++) {
-          const unsigned long long *tl = &rows[(size_t)g * SDR_PROF_SLOTS + 128 + (st * SDR_STAGES + w) * 4];
-          fprintf(stderr, " [%d: %llu %llu %llu %llu]", w, tl[0], tl[1], tl[2], tl[3]);
-        }
-        fprintf(stderr, "\n");
-      }
+    for (int e = 0; e < SDR_STAGES; e++) h->prof_bar[cls * SDR_STAGES + e] += rows[(size_t)g * SDR_PROF_SLOTS + 16 + e];
     h->prof_groups[cls] += h->prof_launches;
   }
   if (dev_zero(h->d_prof, rows.size() * 8, h->last_stream)) return SDR_ERR_CUDA;
@@ -460,6 +495,8 @@ void sdr_batch_destroy(sdr_batch_t *h) {
     dev_event_destroy(h->ev_h2d[k]); dev_event_destroy(h->ev_comp[k]); dev_event_destroy(h->ev_d2h[k]);
   }
   dev_stream_destroy(h->s_h2d); dev_stream_destroy(h->s_comp); dev_stream_destroy(h->s_d2h);
+  for (int k = 0; k < 8; k++) { if (h->s_aux[k]) dev_sync(h->s_aux[k]); dev_stream_destroy(h->s_aux[k]); dev_event_destroy(h->ev_join[k]); }
+  dev_event_destroy(h->ev_fork);
   dev_free(h->d_prof);
   delete h;
 }
@@ -480,6 +517,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->s_h2d = h->s_comp = h->s_d2h = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0;
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
+  h->ev_fork = nullptr; for (int k = 0; k < 8; k++) { h->s_aux[k] = nullptr; h->ev_join[k] = nullptr; }
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
   h->prof_busy.assign(2 * SDR_STAGES, 0); h->prof_crit.assign(32, 0); h->prof_bar.assign(2 * SDR_STAGES, 0); h->prof_extra.assign(16, 0); h->prof_load.assign(2 * (SDR_STAGES + 1), 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
@@ -547,30 +585,21 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
   if (!h) return fail(SDR_ERR_ARG, "null handle");
   if (n_blocks == 0) return fail(SDR_ERR_ARG, "n_blocks == 0");
   if (h->desc.max_blocks_per_call && n_blocks > h->desc.max_blocks_per_call) return fail(SDR_ERR_ARG, "n_blocks > max_blocks_per_call");
-  if (n_blocks > (1u << 28)) return fail(SDR_ERR_ARG, "n_blocks too large");
+  if (n_blocks > (1u << 24)) return fail(SDR_ERR_ARG, "n_blocks too large (at most 2^24 blocks per call)");
   int rc;
   if ((rc = check_plane(I, in_pitch, in_fmt, n_blocks, "I")) || (rc = check_plane(Q, in_pitch, in_fmt, n_blocks, "Q")) ||
       (rc = check_plane(audio, out_pitch, out_fmt, n_blocks, "audio")))
     return rc;
   if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  /* configuration uploads, state resets and the kernels of this call must not overtake work an earlier call queued on
+   * another stream (they share the handle's state and tables) */
+  if (h->launches && stream != h->last_stream && dev_sync(h->last_stream)) return SDR_ERR_CUDA;
   if ((rc = sync_config(h, stream)) != 0) return rc;
   SdrLaunch L;
   memset(&L, 0, sizeof L);
-  L.map_ssb = SDR_MAP_SSB_DEFAULT; L.map_env = SDR_MAP_ENV_DEFAULT;
-  { /* diagnostics: alternative stage placement; a map must name each of the 14 stages exactly once */
-    const char *names[2] = {"SDR_MAP_SSB", "SDR_MAP_ENV"};
-    unsigned long long *dst[2] = {&L.map_ssb, &L.map_env};
-    for (int k = 0; k < 2; k++) if (const char *e = getenv(names[k])) {
-      const unsigned long long m = strtoull(e, nullptr, 16);
-      unsigned seen = 0;
-      for (int w = 0; w < SDR_STAGES; w++) seen |= 1u << ((m >> (4 * w)) & 15);
-      if (seen == (1u << SDR_STAGES) - 1) *dst[k] = m;
-    }
-  }
   L.in_i = I; L.in_q = Q; L.out = audio; L.in_pitch = in_pitch; L.out_pitch = out_pitch; L.in_fmt = in_fmt; L.out_fmt = out_fmt;
-  L.n_tiles = n_blocks * SDR_TPB; L.blk0_mod3 = (uint32_t)(h->blocks_done % 3);
-  L.cfg = h->d_cfg; L.state = h->d_state; L.ch_stride = h->ch_stride; L.groups = h->d_groups; L.agc_luts = h->d_luts; L.tabs = h->d_tabs;
-  L.n_groups = h->n_groups;
+  L.blk0_mod3 = (uint32_t)(h->blocks_done % 3);
+  L.cfg = h->d_cfg; L.state = h->d_state; L.ch_stride = h->ch_stride; L.agc_luts = h->d_luts; L.tabs = h->d_tabs;
   if (h->prof_on) {
     size_t need = (size_t)std::max<uint32_t>(h->n_groups, 1) * SDR_PROF_SLOTS * 8;
     if (need > h->prof_cap) {
@@ -578,12 +607,31 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
       if (dev_alloc((void **)&h->d_prof, need) || dev_zero(h->d_prof, need, stream)) return SDR_ERR_NOMEM;
       h->prof_cap = need;
     }
-    L.prof = h->d_prof; h->prof_launches++;
+    h->prof_launches++;
     if (const char *e = getenv("SDR_DIAG_SKIP")) L.diag_skip = (uint32_t)strtoul(e, nullptr, 16); /* time stages in isolation */
   }
-  int e = sdrk_launch_pipeline(&L, stream);
-  if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
-  h->launches++;
+  /* one launch per bucket; the first on the caller's stream, the others on streams forked from it and joined back, so
+   * that the buckets of a mixed handle share the GPU instead of queueing behind each other */
+  const size_t nbk = h->buckets.size();
+  if (nbk > 1) {
+    if (!h->ev_fork) {
+      if (dev_event_create(&h->ev_fork)) return SDR_ERR_CUDA;
+      for (int k = 0; k < 8; k++) if (dev_stream_create(&h->s_aux[k]) || dev_event_create(&h->ev_join[k])) return SDR_ERR_CUDA;
+    }
+    if (dev_event_record(h->ev_fork, stream)) return SDR_ERR_CUDA;
+  }
+  for (size_t k = 0; k < nbk; k++) {
+    const Bucket &b = h->buckets[k];
+    void *s = k == 0 ? stream : h->s_aux[k - 1];
+    if (k > 0 && dev_stream_wait(s, h->ev_fork)) return SDR_ERR_CUDA;
+    L.lay = b.lay; L.groups = h->d_groups + b.first; L.n_groups = b.count;
+    L.n_tiles = n_blocks * (uint32_t)b.lay.tpb;
+    L.prof = h->prof_on ? h->d_prof + (size_t)b.first * SDR_PROF_SLOTS : nullptr;
+    int e = sdrk_launch_pipeline(&L, s);
+    if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
+    h->launches++;
+    if (k > 0 && (dev_event_record(h->ev_join[k - 1], s) || dev_stream_wait(stream, h->ev_join[k - 1]))) return SDR_ERR_CUDA;
+  }
   h->blocks_done += n_blocks;
   h->last_stream = stream;
   return SDR_OK;
@@ -720,20 +768,9 @@ int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy28, uint64_t *total
   if (getenv("SDR_ROLE_PROFILE_NB"))
     for (int cls = 0; cls < 2; cls++)
       if (h->prof_groups[cls]) {
-        fprintf(stderr, "[sdr] class %d: cycles per CTA launch: prologue %.0f, pipeline %.0f; state-load cycles per stage:", cls,
+        fprintf(stderr, "[sdr] class %d: cycles per CTA launch: prologue %.0f, pipeline %.0f; share of it each stage spent waiting for other stages:", cls,
                 (double)h->prof_load[cls * (SDR_STAGES + 1) + SDR_STAGES] / h->prof_groups[cls], (double)h->prof_total[cls] / h->prof_groups[cls]);
-        for (int w = 0; w < SDR_STAGES; w++) fprintf(stderr, " %.0f", (double)h->prof_load[cls * (SDR_STAGES + 1) + w] / h->prof_groups[cls]);
-        fprintf(stderr, "\n");
-      }
-  if (getenv("SDR_ROLE_PROFILE_NB"))
-    for (int cls = 0; cls < 2; cls++)
-      if (h->prof_crit[cls * 16 + 15]) {
-        const double steps = (double)h->prof_crit[cls * 16 + 15];
-        fprintf(stderr, "[sdr] class %d: slowest stage of a step: mean %.0f cycles; share of steps in which each stage was the slowest:", cls,
-                (double)h->prof_crit[cls * 16 + 14] / steps);
-        for (int w = 0; w < SDR_STAGES; w++) fprintf(stderr, " %.3f", (double)h->prof_crit[cls * 16 + w] / steps);
-        fprintf(stderr, "\n[sdr] class %d: cycles per step at the barrier, per stage:", cls);
-        for (int w = 0; w < SDR_STAGES; w++) fprintf(stderr, " %.0f", (double)h->prof_bar[cls * SDR_STAGES + w] / steps);
+        for (int w = 0; w < SDR_STAGES; w++) fprintf(stderr, " %.3f", (double)h->prof_bar[cls * SDR_STAGES + w] / (double)std::max<uint64_t>(h->prof_total[cls], 1));
         fprintf(stderr, "\n");
       }
   if (getenv("SDR_ROLE_PROFILE_NB") && h->prof_total[0])

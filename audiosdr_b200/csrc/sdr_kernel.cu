@@ -1,7 +1,7 @@
 /* sdr_kernel.cu -- sm_100a kernels of the batched receiver chain and their launchers.
  *
- * sdr_pipeline_kernel: one CTA per 32-channel group, 14 warps = 14 pipeline stages (see
- * sdr_pipeline.cuh).  Build flags matter for parity: -fmad=false (no FMA contraction; the reference
+ * sdr_pipeline_kernel: one CTA per 32-channel group, one warp per pipeline stage of the launch's bucket (see
+ * sdr_pipeline.cuh, sdr_lay.h).  Build flags matter for parity: -fmad=false (no FMA contraction; the reference
  * rounds every product and sum separately), IEEE division and square root (nvcc defaults), no FTZ.
  */
 #include <cuda_runtime.h>
@@ -14,117 +14,94 @@ using namespace sdrk;
 
 __constant__ float2 c_hilbert2[64]; /* compact Hilbert half, H:757-774, every tap twice: the multiplicand pairs of the packed FIR */
 
-/* CTA-wide step barrier.  Every warp is a different stage and reaches the barrier from a different instruction, so the
- * unaligned form (`barrier.sync`, sm_70+) is used after re-converging the warp: lanes of an incompletely filled group
- * leave their stage body early. */
-__device__ __forceinline__ void step_barrier() {
+/* ---- stage-to-stage hand-over (sdr_lay.h): one mbarrier per (stage, tile mod SDR_BAR_W), arrival count 1.  A stage
+ * signals a finished tile with one arrive by lane 0 after re-converging the warp (the warp barrier orders the other
+ * lanes' shared-memory and global writes before the arrive, whose release semantics publish them to the waiting
+ * stages); a waiting stage polls the barrier's phase parity with mbarrier.try_wait (acquire), which suspends the warp in
+ * hardware instead of spinning in the issue slots of the stages that share its scheduler. */
+__device__ __forceinline__ void bar_init(uint32_t addr, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+/* CTA-wide barrier of warps that arrive from different instructions (every warp is a different stage): the unaligned
+ * form after re-converging the warp.  Used once per launch, between the stages' state loads and their tile loops. */
+__device__ __forceinline__ void cta_barrier() {
   __syncwarp();
   asm volatile("barrier.sync 0;" ::: "memory");
 }
 
 template <class Body>
-__device__ __forceinline__ void pipeline_loop(const Ctx &x, int role, uint32_t n_tiles, int delay, int dmax, Body body) {
+__device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body) {
   unsigned long long *prof = x.prof ? x.L->prof : nullptr; /* nullptr at compile time in the product kernel */
   const long long t_loaded = prof ? clock64() : 0;
-  step_barrier(); /* histories and tables are in shared memory */
-  const uint32_t steps = n_tiles + (uint32_t)dmax;
-  long long busy = 0, at_barrier = 0, t_begin = prof ? clock64() : 0;
-  uint16_t *scr = reinterpret_cast<uint16_t *>(x.smem + S_PROFSCR);
-  long long t_rel = t_begin; /* release of the previous step barrier, as this warp saw it */
+  cta_barrier(); /* histories and tables are in shared memory */
+  const uint32_t n = x.L->n_tiles, tpbm = (uint32_t)(x.Y->tpb - 1);
+  const uint32_t bars = (uint32_t)__cvta_generic_to_shared(x.smem + x.Y->o_bar);
+  const bool skip = prof && ((x.L->diag_skip >> stage) & 1u);
+  long long busy = 0, waiting = 0;
+  const long long t_begin = prof ? clock64() : 0;
 #pragma unroll 1
-  for (uint32_t s = 0; s < steps; s++) {
-    const long long tau = (long long)s - delay;
-    long long b = 0, t0 = 0, t1 = 0;
-    if (tau >= 0 && tau < (long long)n_tiles && !(prof && ((x.L->diag_skip >> role) & 1u))) {
-      t0 = prof ? clock64() : 0;
-      body((uint32_t)tau);
-      if (prof) { t1 = clock64(); b = t1 - t0; busy += b; }
+  for (uint32_t t = 0; t < n; t++) {
+    const long long tw = prof ? clock64() : 0;
+#pragma unroll 1
+    for (int i = 0; i < SDR_MAX_DEPS; i++) {
+      const SdrDep d = x.Y->deps[stage][i];
+      if (d.stage < 0) break;
+      const long long u = d.kind ? (long long)(t | tpbm) : (long long)t + d.k;
+      if (u < 0) continue;
+      bar_wait(bars + (uint32_t)(d.stage * SDR_BAR_W + ((uint32_t)u & (SDR_BAR_W - 1))) * 8u, ((uint32_t)u / SDR_BAR_W) & 1u);
     }
-    if (prof && (threadIdx.x & 31) == 0) scr[(s & 1) * 16 + role] = (uint16_t)(b >> 4);
-    const long long tb = prof ? clock64() : 0;
-    step_barrier();
-    if (prof) {
-      const long long te = clock64();
-      at_barrier += te - tb;
-      if (s >= 200 && s < 204 && (threadIdx.x & 31) == 0) { /* time line: body start, body end, barrier arrival, release; relative to the previous release */
-        unsigned long long *tl = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS + 128 + ((s - 200) * SDR_STAGES + role) * 4;
-        tl[0] = (unsigned long long)(t0 - t_rel); tl[1] = (unsigned long long)(t1 - t_rel); tl[2] = (unsigned long long)(tb - t_rel); tl[3] = (unsigned long long)(te - t_rel);
-      }
-      t_rel = te;
-    }
-    if (prof && role == 0 && (threadIdx.x & 31) == 0) { /* which stage did this step wait for? */
-      uint32_t mx = 0; int arg = 0;
-      for (int w = 0; w < SDR_STAGES; w++) { const uint32_t v = (uint32_t)scr[(s & 1) * 16 + w] << 4; if (v > mx) { mx = v; arg = w; } }
-      unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
-      row[40 + arg] += 1; row[54] += mx; row[55] += 1;
-    }
+    const long long t0 = prof ? clock64() : 0;
+    if (!skip) body(t);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) bar_arrive(bars + (uint32_t)(stage * SDR_BAR_W + (t & (SDR_BAR_W - 1))) * 8u);
+    if (prof) { const long long t1 = clock64(); waiting += t0 - tw; busy += t1 - t0; }
   }
   if (prof && (threadIdx.x & 31) == 0) {
     unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
-    row[role] += (unsigned long long)busy;
-    row[64 + role] += (unsigned long long)at_barrier;                          /* cycles between this stage's arrival at the step barriers and its release */
-    row[16 + role] += (unsigned long long)(t_loaded - x.t0);                 /* this stage's state load */
-    if (threadIdx.x == 0) { row[14] += (unsigned long long)(clock64() - t_begin); row[15] += (unsigned long long)(t_begin - x.t0); }
+    row[stage] += (unsigned long long)busy;
+    row[16 + stage] += (unsigned long long)waiting;
+    if (x.Y->stage_of_warp[0] == stage) { row[14] += (unsigned long long)(clock64() - t_begin); row[15] += (unsigned long long)(t_loaded - x.t0); }
   }
 }
 
-/* One warp = one stage.  Stages common to both pipeline classes are instantiated once (offsets and delays
- * are run-time values) to keep the kernel's instruction footprint small: every warp runs different code, so
- * the hot loops of all 14 stages have to share the instruction caches. */
-__device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
-  const uint32_t n = x.L->n_tiles;
-  const bool ssb = x.G->cls == CLS_SSB;
-  const int dmax = ssb ? (int)D_SSB_MAX : (int)D_ENV_MAX;
+/* One warp = one stage.  Stages common to both pipeline classes are instantiated once (ring offsets are run-time
+ * values of the launch's plan) to keep the kernel's instruction footprint small: every warp runs different code, so
+ * the hot loops of all stages have to share the instruction caches. */
+__device__ __forceinline__ void run_stage(const Ctx &x, int stage, int lane) {
+  const bool ssb = x.Y->cls == CLS_SSB;
   /* every 4-section cascade of the chain (IF rails, audio band-pass, AM image rails) runs through this one site */
-  const bool is_if = warp == 2 || warp == 3, is_aud = warp == 9, is_img = !ssb && (warp == 6 || warp == 7);
+  const bool is_if = stage == ST_IFI || stage == ST_IFQ, is_aud = stage == ST_AUD, is_img = !ssb && (stage == ST_IMGI || stage == ST_IMGQ);
   if (is_if || is_aud || is_img) {
-    const int kind = is_if ? 0 : (is_aud ? 1 : 2), rail = is_if ? warp - 2 : (is_img ? warp - 6 : 0);
-    /* tile of step t: base + ((t % cycle) * per + rail) tiles */
-    const int src = is_if ? (int)S_X : (is_aud ? (ssb ? (int)S_A : (int)E_A) : (int)E_Z2);
-    const int dst = is_if ? (int)S_Y : (is_aud ? (ssb ? (int)S_B : (int)E_B) : (int)E_V); /* audio and image filters work in place */
-    const int s_per = is_aud ? 1 : 2, d_per = is_aud ? 1 : 2;
-    const int a_cyc = ssb ? (int)NA : (int)NB_RING;
-    const int s_cyc = is_img ? (int)NZ2 : (is_if ? (int)NR : a_cyc); /* all three kinds filter in place: source cycle = destination cycle */
-    const int delay = is_if ? (int)D_IF : (is_aud ? (ssb ? (int)D_AUD : (int)E_D_AUD) : (int)E_D_IMG);
-    RoleBiquad r; r.load(x, lane, kind, rail);
-    int slot = 0; /* t % s_cyc, counted (the stage's tiles are t = 0, 1, 2, ...; the cycle length is a run-time value) */
-    pipeline_loop(x, warp, n, delay, dmax, [&](uint32_t t) {
-      const bool run = is_if ? true : (is_aud ? r.on : (r.cid >= 0 && env_flag(x, lane, t) != 0));
-      r.step(x.tile(src, slot * s_per + rail), x.tile(dst, slot * d_per + rail), lane, run);
-      slot = slot + 1 == s_cyc ? 0 : slot + 1;
-    });
-    r.save(x, kind, rail);
+    RoleBiquad r; r.load(x, lane, is_if ? 0 : (is_aud ? 1 : 2), is_if ? stage - ST_IFI : (is_img ? stage - ST_IMGI : 0));
+    pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, lane, t); });
+    r.save(x);
     return;
   }
-  switch (warp) {
-    case 0: {
+  switch (stage) {
+    case ST_IN: {
       RoleIn r; r.load(x, lane);
-      pipeline_loop(x, warp, n, D_IN, dmax, [&](uint32_t t) { r.step_a(x, lane, t); __syncwarp(); r.step_b(x, lane, t); });
+      pipeline_loop(x, stage, [&](uint32_t t) { r.step_a(x, lane, t); __syncwarp(); r.step_b(x, lane, t); });
       r.save(x, lane);
     } break;
-    case 1: { RoleNb r; r.load(x, lane); pipeline_loop(x, warp, n, D_NB, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
-    case 12: { RoleEnvl r; r.load(x, lane); pipeline_loop(x, warp, n, D_ENVL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); } break;
-    case 13: { RoleNbo r; r.load(x, lane); pipeline_loop(x, warp, n, D_NBO, dmax, [&](uint32_t t) { r.step(x, lane, t); }); } break;
-    case 10: {
-      RoleAgc r; r.load(x, lane);
-      const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? (int)NA : (int)NB_RING, dst = ssb ? (int)S_C : (int)E_C;
-      int ss = 0, ds = 0; /* t % ns and t % NC, counted (ns is a run-time value) */
-      pipeline_loop(x, warp, n, ssb ? (int)D_AGC : (int)E_D_AGC, dmax, [&](uint32_t t) {
-        const float carrier = ssb ? 0.0f : x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane];
-        r.step(x.tile(src, ss), x.tile(dst, ds), lane, carrier);
-        ss = ss + 1 == ns ? 0 : ss + 1; ds = ds + 1 == (int)NC ? 0 : ds + 1;
-      });
-      r.save(x);
-    } break;
-    case 11: {
-      const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
-      RoleOut r; r.load(x, lane, oc, oa);
-      pipeline_loop(x, warp, n, ssb ? (int)D_OUT : (int)E_D_OUT, dmax, [&](uint32_t t) { r.step_a(x, lane, t, oc, oa); __syncwarp(); r.step_b(x, lane, t); __syncwarp(); });
-      r.save(x, lane, oc, oa);
+    case ST_NB: { RoleNb r; r.load(x, lane); pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x, lane); } break;
+    case ST_ENVL: { RoleEnvl r; r.load(x, lane); pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, lane, t); }); } break;
+    case ST_NBO: { RoleNbo r; r.load(x, lane); pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, lane, t); }); } break;
+    case ST_AGC: { RoleAgc r; r.load(x, lane); pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); } break;
+    case ST_OUT: {
+      RoleOut r; r.load(x, lane);
+      pipeline_loop(x, stage, [&](uint32_t t) { r.step_a(x, lane, t); __syncwarp(); r.step_b(x, lane, t); __syncwarp(); });
+      r.save(x, lane);
     } break;
     default:
       if (ssb) {
-        if (warp == 4) {
+        if (stage == ST_NCO) {
           RoleNco r; r.load(x, lane);
           { /* does every active lane run the same oscillator? then one table per tile serves the whole group */
             const unsigned act = __ballot_sync(0xffffffffu, r.cid >= 0);
@@ -133,21 +110,21 @@ __device__ __forceinline__ void run_group(const Ctx &x, int warp, int lane) {
             r.uniform = __all_sync(0xffffffffu, r.cid < 0 || (f2u(r.phase) == pb && f2u(r.inc) == ib)) != 0;
             if (r.uniform) { r.phase = u2f(pb); r.inc = u2f(ib); }
           }
-          pipeline_loop(x, warp, n, D_NCO, dmax, [&](uint32_t t) {
+          pipeline_loop(x, stage, [&](uint32_t t) {
             if (r.uniform) { r.table_step(x, lane); __syncwarp(); r.mix_step(x, lane, t); }
             else r.step(x, lane, t);
           });
           r.save(x);
         } else {
-          const int sub = warp - 5;
+          const int sub = stage - ST_HIL0;
           RoleHilbert r; r.load(x, lane, sub);
-          pipeline_loop(x, warp, n, D_HIL, dmax, [&](uint32_t t) { r.step(x, reinterpret_cast<const float *>(c_hilbert2), lane, sub, t); });
+          pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, reinterpret_cast<const float *>(c_hilbert2), lane, sub, t); });
           r.save(x, lane, sub);
         }
       } else {
-        if (warp == 4) { RolePll r; r.load(x, lane); pipeline_loop(x, warp, n, E_D_PLL, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
-        else if (warp == 5) { RoleNco2 r; r.load(x, lane); pipeline_loop(x, warp, n, E_D_NCO2, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
-        else { RoleMag r; r.load(x, lane); pipeline_loop(x, warp, n, E_D_MAG, dmax, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        if (stage == ST_PLL) { RolePll r; r.load(x, lane); pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else if (stage == ST_NCO2) { RoleNco2 r; r.load(x, lane); pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
+        else { RoleMag r; r.load(x, lane); pipeline_loop(x, stage, [&](uint32_t t) { r.step(x, lane, t); }); r.save(x); }
       }
       break;
   }
@@ -157,40 +134,41 @@ template <bool PROF>
 __device__ __forceinline__ void pipeline_cta(const SdrLaunch &L, unsigned char *smem) {
   Ctx x;
   x.L = &L;
+  x.Y = &L.lay;
   x.G = &L.groups[blockIdx.x];
   x.smem = smem;
   x.gidx = (int)blockIdx.x;
   x.prof = PROF;
   x.t0 = PROF ? clock64() : 0;
-  for (int i = threadIdx.x; i < 257; i += SDR_THREADS) x.f(S_SINE)[i] = L.tabs->sine[i];
-  if (threadIdx.x < SDR_LANES) reinterpret_cast<int *>(smem + S_CID)[threadIdx.x] = x.G->cid[threadIdx.x];
-  __syncthreads(); /* stage IN requests its first tile from load(), which needs the channel ids */
-  for (int i = threadIdx.x; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i += SDR_THREADS) { /* the group's AGC tables */
-    const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];
-    if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
+  const int nthr = (int)blockDim.x;
+  for (int i = threadIdx.x; i < 257; i += nthr) x.f(x.Y->o_sine)[i] = L.tabs->sine[i];
+  if (threadIdx.x < SDR_LANES) reinterpret_cast<int *>(smem + x.Y->o_cid)[threadIdx.x] = x.G->cid[threadIdx.x];
+  {
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem + x.Y->o_bar);
+    for (int i = threadIdx.x; i < SDR_STAGES * SDR_BAR_W; i += nthr) bar_init(bars + 8u * (uint32_t)i, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  /* Physical warp -> stage.  The warp scheduler of an SM sub-partition favours the HIGHER warp id among eligible
-   * warps, and warp id % 4 picks the sub-partition (two of them hold four warps, two hold three), so the placement
-   * decides which stages compete for one scheduler and who wins.  Stage numbering (the `warp` argument of
-   * run_group): 0 IN, 1 NB scan, 2/3 IF-I/IF-Q, 4..8 class specific (SSB: NCO, Hilbert x4; ENV: PLL, NCO2, image I/Q,
-   * envelope), 9 audio BPF, 10 AGC, 11 ALS+OUT, 12 ENVL, 13 NB-out. */
+  __syncthreads(); /* stage IN requests its first tile from load(), which needs the channel ids */
+  for (int i = threadIdx.x; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i += nthr) { /* the group's AGC tables */
+    const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];
+    if (id >= 0) x.f(x.Y->o_lut)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
+  }
+  /* Physical warp -> stage (SdrLay::stage_of_warp).  The warp scheduler of an SM sub-partition favours the HIGHER warp id
+   * among eligible warps, and warp id % 4 picks the sub-partition, so the placement decides which stages compete for one
+   * scheduler and who wins; the defaults for the 14-stage launches (sdr_types.h) were found by measurement
+   * (tools/map_search.py). */
   const int phys = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  /* The default placements (sdr_types.h) were found by measurement (tools/map_search.py, hill climbing over pair swaps with
-   * CUDA-event timing of the bench workload): SSB 0x3BADC548961720 = sub-partition 0 {IN, Hilbert, Hilbert, OUT},
-   * 1 {IF-I, audio BPF, ENVL, IF-Q}, 2 {Hilbert, Hilbert, NB-out}, 3 {NB scan, NCO, AGC} -- 16 % faster than a placement
-   * balanced by instruction count: the short latency-bound chains (blanker scan, AGC) want a sub-partition to themselves. */
-  const int stage = (int)(((x.G->cls == CLS_SSB ? L.map_ssb : L.map_env) >> (4 * phys)) & 15);
-  run_group(x, stage, lane);
+  run_stage(x, (int)x.Y->stage_of_warp[phys], lane);
 }
 
-/* The product kernel and its diagnostics twin (per-stage busy counters, sub-phase timers, stage skipping): the twin is
- * launched only when the handle was created with SDR_ROLE_PROFILE=1.  Keeping the counters out of the product kernel is
- * not cosmetic: its stages are 14 different instruction streams whose loops must share the instruction caches. */
-extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_kernel(const __grid_constant__ SdrLaunch L) {
+/* The product kernel and its diagnostics twin (per-stage busy / waiting counters, sub-phase timers, stage skipping): the
+ * twin is launched only when the handle was created with SDR_ROLE_PROFILE=1.  Keeping the counters out of the product
+ * kernel is not cosmetic: its stages are different instruction streams whose loops must share the instruction caches. */
+extern "C" __global__ void __launch_bounds__(SDR_THREADS_MAX, 1) sdr_pipeline_kernel(const __grid_constant__ SdrLaunch L) {
   extern __shared__ __align__(16) unsigned char smem[];
   pipeline_cta<false>(L, smem);
 }
-extern "C" __global__ void __launch_bounds__(SDR_THREADS, 1) sdr_pipeline_prof_kernel(const __grid_constant__ SdrLaunch L) {
+extern "C" __global__ void __launch_bounds__(SDR_THREADS_MAX, 1) sdr_pipeline_prof_kernel(const __grid_constant__ SdrLaunch L) {
   extern __shared__ __align__(16) unsigned char smem[];
   pipeline_cta<true>(L, smem);
 }
@@ -239,16 +217,22 @@ extern "C" int sdrk_setup_device(const float *hilbert64) {
   for (int i = 0; i < 64; i++) h2[i] = make_float2(hilbert64[i], hilbert64[i]);
   cudaError_t e = cudaMemcpyToSymbol(c_hilbert2, h2, sizeof h2);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(sdr_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDR_SMEM_BYTES);
+  e = cudaFuncSetAttribute(sdr_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(sdr_pipeline_prof_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDR_SMEM_BYTES);
+  e = cudaFuncSetAttribute(sdr_pipeline_prof_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (e != cudaSuccess) return (int)e;
+  /* launches that need less than half of an SM's shared memory are meant to share the SM: keep the carve-out at its maximum */
+  e = cudaFuncSetAttribute(sdr_pipeline_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(sdr_pipeline_prof_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   return (int)e;
 }
 
 extern "C" int sdrk_launch_pipeline(const SdrLaunch *L, void *stream) {
   if (L->n_groups == 0) return 0;
-  if (L->prof) sdr_pipeline_prof_kernel<<<L->n_groups, SDR_THREADS, SDR_SMEM_BYTES, (cudaStream_t)stream>>>(*L);
-  else sdr_pipeline_kernel<<<L->n_groups, SDR_THREADS, SDR_SMEM_BYTES, (cudaStream_t)stream>>>(*L);
+  const int threads = L->lay.n_warps * 32, smem = L->lay.smem_bytes;
+  if (L->prof) sdr_pipeline_prof_kernel<<<L->n_groups, threads, smem, (cudaStream_t)stream>>>(*L);
+  else sdr_pipeline_kernel<<<L->n_groups, threads, smem, (cudaStream_t)stream>>>(*L);
   return (int)cudaGetLastError();
 }
 

@@ -1,0 +1,233 @@
+/* sdr_lay.h -- shared-memory plan and hand-over rules of one pipeline launch.
+ *
+ * A launch covers the groups of ONE bucket: a pipeline class (SSB: NCO + Hilbert; ENV: PLL + envelope) with one set of
+ * optional stages (blanker trio; ALS history).  For that bucket lay_build() decides
+ *   - the tile length T (samples a stage works on at a time: 32, 16 or 8; 128 / T tiles make one reference block),
+ *   - which stages exist and which warp runs which stage,
+ *   - where every ring and table lives in the CTA's shared memory and how many tiles each ring holds,
+ *   - for every stage, which tiles of which other stages it has to wait for (SdrDep).
+ * The stages of a group are NOT stepped in lock step: stage X starts tile t as soon as every stage it depends on has
+ * finished the tiles named by its rules -- producers for data (read-after-write), consumers for ring slots
+ * (write-after-read) -- signalled through one mbarrier per (stage, tile mod SDR_BAR_W).  The lock-step schedule "stage
+ * with delay d works on tile s - d at step s" is one valid order of that partial order (lay_check() proves it for the
+ * rules built here: every rule points to an earlier step), so the rules cannot deadlock, and ring depths beyond the
+ * minimum only add slack between neighbours.
+ *
+ * Plain C-style header: compiled into the product (sdr_host.cpp, sdr_kernel.cu) and into the host emulation of the
+ * test suite (tests/emu), which runs the same rules with adversarial schedules.
+ */
+#ifndef SDR_LAY_H
+#define SDR_LAY_H
+#include <stdint.h>
+#include <string.h>
+
+#include "sdr_types.h"
+
+/* stage ids (= the `stage` argument of run_stage; a launch's warps map onto a subset of them) */
+enum {
+  ST_IN = 0, ST_NB = 1, ST_IFI = 2, ST_IFQ = 3,
+  ST_NCO = 4, ST_HIL0 = 5, /* .. ST_HIL0 + 3 */
+  ST_PLL = 4, ST_NCO2 = 5, ST_IMGI = 6, ST_IMGQ = 7, ST_MAG = 8,
+  ST_AUD = 9, ST_AGC = 10, ST_OUT = 11, ST_ENVL = 12, ST_NBO = 13
+};
+
+/* bucket features */
+enum { LF_NB = 1u, LF_ALS = 2u };
+
+static inline int lay_align(int v, int a) { return (v + a - 1) / a * a; }
+
+#ifdef SDR_EMU
+#include <stdlib.h>
+/* test scaffold only (tests/emu): SDR_EMU_DROP_RULE=n leaves out the n-th rule of every plan, to show that the
+ * adversarial schedules of the emulation notice a missing rule */
+static int lay_emu_rule_counter = 0;
+#endif
+
+static inline void lay_dep(SdrLay *L, int stage, int on, int kind, int k) {
+  if (!L->active[on] || !L->active[stage]) return;
+#ifdef SDR_EMU
+  { const char *e = getenv("SDR_EMU_DROP_RULE"); if (e && *e && atoi(e) == lay_emu_rule_counter++) return; }
+#endif
+  for (int i = 0; i < SDR_MAX_DEPS; i++)
+    if (L->deps[stage][i].stage < 0) { L->deps[stage][i].stage = (int8_t)on; L->deps[stage][i].kind = (int8_t)kind; L->deps[stage][i].k = (int16_t)k; return; }
+  L->error = 1; /* table too small */
+}
+
+/* The rule set as ring depths stand in *L (called by lay_build after the depths are final). */
+static inline void lay_rules(SdrLay *L) {
+#ifdef SDR_EMU
+  lay_emu_rule_counter = 0;
+#endif
+  for (int s = 0; s < SDR_STAGES; s++) for (int i = 0; i < SDR_MAX_DEPS; i++) { L->deps[s][i].stage = -1; L->deps[s][i].kind = 0; L->deps[s][i].k = 0; }
+  const int nb = (L->feat & LF_NB) != 0, tpb = L->tpb;
+  const int x0 = L->cls == CLS_SSB ? ST_NCO : ST_PLL; /* the last stage that touches an input-ring slot */
+  /* input ring R (in place): IN -> [ENVL reads, NB-out overwrites] -> IF-I, IF-Q -> NCO / PLL */
+  lay_dep(L, ST_IN, x0, 0, -L->nr);
+  if (nb) {
+    /* blanker, C:606-650.  HBM ring planes: IN writes I/Q of block B into slot B % 3, whose previous content (block B - 3)
+     * NB-out fetched one block (tpb tiles) ago; ENVL does the same for the envelope plane, read by the scan up to the
+     * first tile of the previous block.  Mask slots in shared memory: NB-out reads the final mask of tile t once the scan
+     * of tile t is over; the scan recycles the oldest mask slot two tiles after NB-out has left it (see RoleNb). */
+    lay_dep(L, ST_IN, ST_NBO, 0, -tpb);
+    lay_dep(L, ST_ENVL, ST_IN, 0, 0);
+    lay_dep(L, ST_ENVL, ST_NB, 0, -tpb);
+    lay_dep(L, ST_NB, ST_ENVL, 0, -2);   /* the envelopes the scan requests at the end of tile t (for tile t + 1) were written by ENVL(t - 2) at the latest */
+    lay_dep(L, ST_NB, ST_NBO, 0, -2);
+    lay_dep(L, ST_NBO, ST_NB, 0, 0);
+    lay_dep(L, ST_NBO, ST_ENVL, 0, 0);   /* overwrites the slot ENVL reads */
+    lay_dep(L, ST_IFI, ST_NBO, 0, 0);
+    lay_dep(L, ST_IFQ, ST_NBO, 0, 0);
+  } else {
+    lay_dep(L, ST_IFI, ST_IN, 0, 0);
+    lay_dep(L, ST_IFQ, ST_IN, 0, 0);
+  }
+  lay_dep(L, x0, ST_IFI, 0, 0);
+  lay_dep(L, x0, ST_IFQ, 0, 0);
+  const int back_c = (L->feat & LF_ALS) ? tpb : 0; /* tiles of AGC output the ALS stage reaches back (C:336, M + delay <= 129) */
+  if (L->cls == CLS_SSB) {
+    /* Hilbert rings: tile u of the Q ring is read by HIL(u .. u + back_q), tile u of the I ring by HIL(u + tpb) */
+    const int back_q = (255 + L->T - 1) / L->T;
+    int lead = L->hq_tiles - back_q;
+    if (L->ni - tpb < lead) lead = L->ni - tpb;
+    for (int h = 0; h < L->n_hil; h++) {
+      lay_dep(L, ST_NCO, ST_HIL0 + h, 0, -lead);
+      lay_dep(L, ST_HIL0 + h, ST_NCO, 0, 0);
+      lay_dep(L, ST_HIL0 + h, ST_AGC, 0, -L->na);
+      lay_dep(L, ST_AUD, ST_HIL0 + h, 0, 0);
+    }
+    lay_dep(L, ST_AGC, ST_AUD, 0, 0);
+  } else {
+    /* The envelope path of a block runs iff the PLL is unlocked after the block's LAST sample (C:130-132): NCO2 waits
+     * for the block's last PLL tile; AM-mode AGC uses the carrier level after the block's envelope loop (C:408-409). */
+    lay_dep(L, ST_PLL, ST_NCO2, 0, -L->nz);
+    lay_dep(L, ST_NCO2, ST_PLL, 1, 0);
+    lay_dep(L, ST_NCO2, ST_MAG, 0, -L->nz2);
+    lay_dep(L, ST_IMGI, ST_NCO2, 0, 0);
+    lay_dep(L, ST_IMGQ, ST_NCO2, 0, 0);
+    lay_dep(L, ST_MAG, ST_IMGI, 0, 0);
+    lay_dep(L, ST_MAG, ST_IMGQ, 0, 0);
+    lay_dep(L, ST_MAG, ST_AGC, 0, -L->na);
+    lay_dep(L, ST_AUD, ST_MAG, 0, 0);
+    lay_dep(L, ST_AGC, ST_AUD, 0, 0);
+    lay_dep(L, ST_AGC, ST_MAG, 1, 0);
+  }
+  lay_dep(L, ST_AGC, ST_OUT, 0, -(L->nc - back_c));
+  lay_dep(L, ST_OUT, ST_AGC, 0, 0);
+}
+
+/* Every rule must point to an earlier step of the lock-step schedule (deadlock freedom, see the header comment).
+ * Barrier phases: stage P signals tile u on barrier (P, u mod SDR_BAR_W), and a waiter tells "tile u done" from "not yet" by
+ * the barrier's phase parity, which is only unambiguous while P cannot finish tile u + SDR_BAR_W before the waiter has seen
+ * tile u.  A consumer is never ahead of its producer and a producer is never more than the ring depth ahead of its
+ * consumer, so it suffices that every ring depth and every backward distance stays below SDR_BAR_W - 2. */
+static inline int lay_check(const SdrLay *L) {
+  if (L->error) return 1;
+  for (int s = 0; s < SDR_STAGES; s++) {
+    if (!L->active[s]) continue;
+    for (int i = 0; i < SDR_MAX_DEPS && L->deps[s][i].stage >= 0; i++) {
+      const SdrDep d = L->deps[s][i];
+      const int k = d.kind ? L->tpb - 1 : d.k; /* worst case of (t | (tpb - 1)) - t */
+      if (!(k + L->delay[d.stage] < L->delay[s])) return 2;
+      if (d.k < -(SDR_BAR_W - 2)) return 3;
+    }
+  }
+  const int lim = SDR_BAR_W - 2;
+  if (L->nr > lim || L->na > lim || L->nc > lim || L->nz > lim || L->nz2 > lim || L->ni > lim || L->tpb + 2 > lim) return 3;
+  if (L->smem_bytes > 232448) return 4;
+  return 0;
+}
+
+/* slack: extra ring slots beyond the lock-step minimum, each ring at most `max_slack`, as long as `budget` bytes allow */
+static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget, int max_slack) {
+  memset(L, 0, sizeof *L);
+  if (T != 32 && T != 16 && T != 8) return 1;
+  if ((feat & (LF_NB | LF_ALS)) && T != 32) return 1; /* the blanker scan and the ALS passes are written for 32-sample tiles */
+  L->cls = cls; L->feat = feat; L->T = T; L->tpb = 128 / T; L->tile_f = T * SDR_LANES;
+  for (int v = L->tpb; v > 1; v >>= 1) L->tpb_sh++;
+  const int tpb = L->tpb, nb = (feat & LF_NB) != 0, als = (feat & LF_ALS) != 0, tile_b = L->tile_f * 4;
+  L->n_hil = cls == CLS_SSB ? T / 8 : 0;
+  /* stages and their lock-step delays */
+  int8_t *d = L->delay;
+  L->active[ST_IN] = 1; d[ST_IN] = 0;
+  if (nb) { L->active[ST_ENVL] = L->active[ST_NB] = L->active[ST_NBO] = 1; d[ST_ENVL] = 1; d[ST_NB] = 1; d[ST_NBO] = 2; }
+  L->active[ST_IFI] = L->active[ST_IFQ] = 1; d[ST_IFI] = d[ST_IFQ] = (int8_t)(nb ? 3 : 1);
+  if (cls == CLS_SSB) {
+    L->active[ST_NCO] = 1; d[ST_NCO] = (int8_t)(d[ST_IFI] + 1);
+    for (int h = 0; h < L->n_hil; h++) { L->active[ST_HIL0 + h] = 1; d[ST_HIL0 + h] = (int8_t)(d[ST_NCO] + 1); }
+    d[ST_AUD] = (int8_t)(d[ST_NCO] + 2); d[ST_AGC] = (int8_t)(d[ST_AUD] + 1);
+  } else {
+    L->active[ST_PLL] = L->active[ST_NCO2] = L->active[ST_IMGI] = L->active[ST_IMGQ] = L->active[ST_MAG] = 1;
+    d[ST_PLL] = (int8_t)(d[ST_IFI] + 1); d[ST_NCO2] = (int8_t)(d[ST_PLL] + tpb); d[ST_IMGI] = d[ST_IMGQ] = (int8_t)(d[ST_NCO2] + 1);
+    d[ST_MAG] = (int8_t)(d[ST_NCO2] + 2); d[ST_AUD] = (int8_t)(d[ST_MAG] + 1); d[ST_AGC] = (int8_t)(d[ST_MAG] + tpb);
+  }
+  L->active[ST_AUD] = L->active[ST_AGC] = L->active[ST_OUT] = 1; d[ST_OUT] = (int8_t)(d[ST_AGC] + 1);
+  for (int s = 0; s < SDR_STAGES; s++) if (L->active[s] && d[s] > L->dmax) L->dmax = d[s];
+  /* minimum ring depths: a tile's slot lives from the writer's step to the last reader's step */
+  const int x0 = cls == CLS_SSB ? ST_NCO : ST_PLL;
+  const int back_q = (255 + T - 1) / T, back_c = als ? tpb : 0;
+  L->nr = d[x0] + 1;
+  L->nc = back_c + 2;
+  if (cls == CLS_SSB) { L->hq_tiles = back_q + 2; L->ni = tpb + 2; L->na = 3; }
+  else { L->nz = tpb + 1; L->nz2 = 3; L->na = tpb + 1; }
+  /* fixed part */
+  int o = 0;
+  L->o_sine = o; o += 1152;
+  L->o_lut = o; o += lay_align(SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE * 4, 128);
+  L->o_ncot = o; o += 256;
+  L->o_cid = o; o += 128;
+  L->o_bar = o; o += SDR_STAGES * SDR_BAR_W * 8;
+  if (cls == CLS_ENV) { L->o_flags = o; o += 8 * SDR_LANES * 4; L->o_carr = o; o += 8 * SDR_LANES * 4; }
+  if (nb) { L->o_nbs = o; o += 32 * SDR_LANES * 16; L->o_mask = o; o += 3 * 128 * SDR_LANES; }
+  if (als) { L->o_alsc = o; o += 128 * SDR_LANES * 4; }
+  L->ins_row = T + 4; /* staging rows padded by 16 bytes: a lane reading its own row with 16-byte loads is bank-conflict free */
+  L->o_ins = o; o += 2 * SDR_LANES * L->ins_row * 4;
+  L->o_outs = o; o += SDR_LANES * L->ins_row * 4;
+  const int fixed = o;
+  /* rings: grow round robin while the budget allows */
+  int *ring[6]; int cost[6]; int n_ring = 0;
+  ring[n_ring] = &L->nr; cost[n_ring++] = 2 * tile_b;
+  ring[n_ring] = &L->na; cost[n_ring++] = tile_b;
+  if (cls == CLS_SSB) { ring[n_ring] = &L->ni; cost[n_ring++] = 2 * tile_b; /* the Q ring grows with it */ }
+  else { ring[n_ring] = &L->nz; cost[n_ring++] = 2 * tile_b; ring[n_ring] = &L->nz2; cost[n_ring++] = 2 * tile_b; }
+  ring[n_ring] = &L->nc; cost[n_ring++] = tile_b;
+  for (int pass = 0; pass < max_slack; pass++) {
+    for (int r = 0; r < n_ring; r++) {
+      int total = fixed + L->nr * 2 * tile_b + L->na * tile_b + L->nc * tile_b;
+      if (cls == CLS_SSB) total += (L->hq_tiles * T / 2 + SDR_HQ_MIRROR) * SDR_LANES * 8 + L->ni * tile_b;
+      else total += L->nz * 2 * tile_b + L->nz2 * 2 * tile_b;
+      if (total + cost[r] > budget) continue;
+      *ring[r] += 1;
+      if (cls == CLS_SSB && ring[r] == &L->ni) L->hq_tiles += 1;
+    }
+  }
+  L->o_r = o; o += L->nr * 2 * tile_b;
+  if (cls == CLS_SSB) {
+    L->hq_rows = L->hq_tiles * T / 2;
+    L->o_hq = o; o += (L->hq_rows + SDR_HQ_MIRROR) * SDR_LANES * 8;
+    L->o_hi = o; o += L->ni * tile_b;
+  } else {
+    L->o_z = o; o += L->nz * 2 * tile_b;
+    L->o_z2 = o; o += L->nz2 * 2 * tile_b;
+  }
+  L->o_a = o; o += L->na * tile_b;
+  L->o_c = o; o += L->nc * tile_b;
+  L->smem_bytes = o;
+  /* warps: one per active stage, in stage order until a measured placement is supplied (lay_place) */
+  L->n_warps = 0;
+  for (int s = 0; s < SDR_STAGES; s++) if (L->active[s]) L->stage_of_warp[L->n_warps++] = (uint8_t)s;
+  lay_rules(L);
+  return lay_check(L);
+}
+
+/* placement: `map` = stage id of physical warp w in bits 4w..4w+3 (as many nibbles as the launch has warps); ignored unless it
+ * names every active stage exactly once */
+static inline int lay_place(SdrLay *L, unsigned long long map) {
+  unsigned seen = 0, want = 0;
+  for (int s = 0; s < SDR_STAGES; s++) if (L->active[s]) want |= 1u << s;
+  for (int w = 0; w < L->n_warps; w++) seen |= 1u << ((map >> (4 * w)) & 15);
+  if (seen != want) return 1;
+  for (int w = 0; w < L->n_warps; w++) L->stage_of_warp[w] = (uint8_t)((map >> (4 * w)) & 15);
+  return 0;
+}
+
+#endif

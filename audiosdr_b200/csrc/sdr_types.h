@@ -13,9 +13,12 @@
 #define SDR_TYPES_H
 #include <stdint.h>
 
-#define SDR_T 32        /* samples per pipeline tile; 4 tiles = one reference block of 128 */
 #define SDR_LANES 32    /* channels per group (one warp lane each) */
-#define SDR_TPB 4       /* tiles per block */
+#define SDR_TMAX 32     /* longest pipeline tile in samples (a launch's tile length is SdrLay::T: 32, 16 or 8; 128 / T tiles = one reference block) */
+#define SDR_STAGES 14   /* pipeline stage ids (sdr_lay.h); a launch runs the subset its bucket needs, one warp each */
+#define SDR_BAR_W 32    /* hand-over barriers per stage: stage s signals tile t on barrier (s, t % SDR_BAR_W) */
+#define SDR_MAX_DEPS 6  /* hand-over rules per stage */
+#define SDR_HQ_MIRROR 7 /* rows of the Hilbert Q ring repeated behind its end (sdr_pipeline.cuh, hq_at) */
 
 /* ---- per-channel state words (reference member it stands for) ---- */
 enum {
@@ -97,32 +100,51 @@ typedef struct {
   float pk_consts[8];      /* {1,1,-1,-1,-0,-0}: multiplicands / addends of the packed FMA forms, deliberately run-time data (sdr_pipeline.cuh, PkConst) */
 } SdrTables;
 
+/* ---- one hand-over rule: before tile t a stage waits until stage `stage` has finished tile t + k (kind 0) or the last tile
+ * of t's block, t | (tpb - 1) (kind 1); tiles below 0 never block.  Built by lay_build() (sdr_lay.h). */
+typedef struct { int8_t stage, kind; int16_t k; } SdrDep;
+
+/* ---- shared-memory plan + hand-over rules of one launch (one bucket = pipeline class x optional stages), sdr_lay.h ---- */
+typedef struct {
+  int32_t cls; uint32_t feat;        /* CLS_*, LF_* */
+  int32_t T, tpb, tpb_sh, tile_f;    /* tile length in samples, tiles per block and its log2, floats per tile (T * 32) */
+  int32_t n_hil;                     /* Hilbert warps (8 outputs of a tile each): T / 8 */
+  int32_t nr, ni, na, nc, nz, nz2;   /* ring depths in tiles: input ring, Hilbert I delay, audio ring, AGC-out / ALS history ring, PLL-out ring, envelope work ring */
+  int32_t hq_tiles, hq_rows;         /* Hilbert Q ring: tiles, rows of sample pairs (= hq_tiles * T / 2) */
+  int32_t ins_row;                   /* floats per row of the input / output staging areas */
+  int32_t o_sine, o_lut, o_ncot, o_cid, o_bar, o_flags, o_carr, o_nbs, o_mask, o_alsc, o_ins, o_outs, o_r, o_hq, o_hi, o_z, o_z2, o_a, o_c;
+  int32_t smem_bytes, n_warps, dmax, error;
+  uint8_t stage_of_warp[16];         /* physical warp -> stage id */
+  uint8_t active[16];                /* stage id -> runs in this launch */
+  int8_t delay[16];                  /* the stage's delay in the lock-step schedule (documentation, deadlock-freedom proof, emulation) */
+  SdrDep deps[SDR_STAGES][SDR_MAX_DEPS];
+} SdrLay;
+
 typedef struct {
   const void *in_i, *in_q;
   void *out;
   unsigned long long in_pitch, out_pitch; /* elements */
   int32_t in_fmt, out_fmt;
-  uint32_t n_tiles;      /* 4 * n_blocks */
+  uint32_t n_tiles;      /* n_blocks * lay.tpb */
   uint32_t blk0_mod3;    /* absolute index of the call's first block, mod 3 (noise-blanker ring slot) */
   const SdrChanCfg *cfg;
   float *state;
   unsigned long long ch_stride;
-  const SdrGroup *groups;
+  const SdrGroup *groups; /* the launch's groups (CTA b runs groups[b]) */
   const float *agc_luts; /* [n_luts][132] */
   const SdrTables *tabs;
   uint32_t n_groups;
-  uint32_t diag_skip;    /* diagnostics (profiling runs only): bit w set = stage w idles; results are then meaningless */
-  unsigned long long *prof; /* optional [n_groups][SDR_PROF_SLOTS]: busy cycles per warp role + CTA total (diagnostics) */
-  unsigned long long map_ssb, map_env; /* physical warp -> stage, 4 bits per warp (see sdr_kernel.cu) */
+  uint32_t diag_skip;    /* diagnostics (profiling runs only): bit s set = stage s idles; results are then meaningless */
+  unsigned long long *prof; /* optional [n_groups][SDR_PROF_SLOTS] (diagnostics twin): busy and waiting cycles per stage */
+  SdrLay lay;
 } SdrLaunch;
 
-/* default placement of the 14 stages on the 14 warps of a CTA (warp id % 4 = SM sub-partition, higher id = preferred by the
- * scheduler); SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */
+/* default placement of the stages on the warps of a CTA (warp id % 4 = SM sub-partition, higher id = preferred by the
+ * scheduler) for the launches that run all 14 stages; SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */
 #define SDR_MAP_SSB_DEFAULT 0x3BADC548961720ull
 #define SDR_MAP_ENV_DEFAULT 0xA0D459B1328C67ull
 
-#define SDR_STAGES 14     /* pipeline stages = warps per CTA */
-#define SDR_PROF_SLOTS 512 /* [0..95] counters, [128..] a time line of four steps of every stage (diagnostics twin only) */
+#define SDR_PROF_SLOTS 64 /* [0..15] busy cycles per stage, [16..31] cycles waiting for other stages, [32] CTA cycles, [33] prologue (diagnostics twin only) */
 
 #define SDR_AGC_LUT_STRIDE 132
 

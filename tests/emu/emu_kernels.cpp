@@ -12,7 +12,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <string>
 #include <vector>
+#include <stdio.h>
 
 #include "../../audiosdr_b200/csrc/sdr_kernel.h"
 #include "../../audiosdr_b200/csrc/sdr_pipeline.cuh"
@@ -29,42 +32,29 @@ struct Warp {
   std::vector<RoleEnvl> envl; std::vector<RoleNbo> nbo;
 };
 
-int delay_of(int cls, int w) {
-  static const int ssb[14] = {D_IN, D_NB, D_IF, D_IF, D_NCO, D_HIL, D_HIL, D_HIL, D_HIL, D_AUD, D_AGC, D_OUT, D_ENVL, D_NBO};
-  static const int env[14] = {D_IN, D_NB, D_IF, D_IF, E_D_PLL, E_D_NCO2, E_D_IMG, E_D_IMG, E_D_MAG, E_D_AUD, E_D_AGC, E_D_OUT, D_ENVL, D_NBO};
-  return cls == CLS_SSB ? ssb[w] : env[w];
-}
-
 /* phase: 0 = load, 1 = step(t) part A, 3 = step(t) part B (stages that exchange data between lanes run in two
- * parts, the kernel separates them with __syncwarp()), 2 = save -- mirrors run_group() of sdr_kernel.cu */
+ * parts, the kernel separates them with __syncwarp()), 2 = save -- mirrors run_stage() of sdr_kernel.cu */
 void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
-  if (phase == 3 && w != 0 && w != 11) return;
-  const bool ssb = x.G->cls == CLS_SSB;
-  const int oc = ssb ? (int)S_C : (int)E_C, oa = ssb ? (int)S_ALSC : (int)E_ALSC;
-  if (w == 0) { k.in.resize(32); RoleIn &r = k.in[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step_a(x, lane, t); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane); }
-  else if (w == 1) { k.nbk.resize(32); RoleNb &r = k.nbk[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }
-  else if (w == 12) { k.envl.resize(32); RoleEnvl &r = k.envl[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); }
-  else if (w == 13) { k.nbo.resize(32); RoleNbo &r = k.nbo[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); }
-  else if (w == 2 || w == 3) {
-    k.bq.resize(32); RoleBiquad &r = k.bq[lane]; const int rail = w - 2;
-    if (phase == 0) r.load(x, lane, 0, rail);
-    else if (phase == 1) r.step(x.tile(S_X, (t % NR) * 2 + rail), x.tile(S_Y, (t % NR) * 2 + rail), lane, true);
-    else r.save(x, 0, rail);
-  } else if (w == 9) {
+  if (phase == 3 && w != ST_IN && w != ST_OUT) return;
+  const bool ssb = x.Y->cls == CLS_SSB;
+  if (w == ST_IN) { k.in.resize(32); RoleIn &r = k.in[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step_a(x, lane, t); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane); }
+  else if (w == ST_NB) { k.nbk.resize(32); RoleNb &r = k.nbk[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }
+  else if (w == ST_ENVL) { k.envl.resize(32); RoleEnvl &r = k.envl[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); }
+  else if (w == ST_NBO) { k.nbo.resize(32); RoleNbo &r = k.nbo[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); }
+  else if (w == ST_IFI || w == ST_IFQ || w == ST_AUD || (!ssb && (w == ST_IMGI || w == ST_IMGQ))) {
     k.bq.resize(32); RoleBiquad &r = k.bq[lane];
-    const int src = ssb ? (int)S_A : (int)E_A, dst = ssb ? (int)S_B : (int)E_B, nd = ssb ? (int)NA : (int)NB_RING;
-    if (phase == 0) r.load(x, lane, 1, 0); else if (phase == 1) r.step(x.tile(src, t % nd), x.tile(dst, t % nd), lane, r.on); else r.save(x, 1, 0);
-  } else if (w == 10) {
-    k.agc.resize(32); RoleAgc &r = k.agc[lane];
-    const int src = ssb ? (int)S_B : (int)E_B, ns = ssb ? (int)NA : (int)NB_RING;
-    if (phase == 0) r.load(x, lane);
-    else if (phase == 1) r.step(x.tile(src, t % ns), x.tile(oc, t % NC), lane, ssb ? 0.0f : x.f(E_CARR)[((t >> 2) & 7) * SDR_LANES + lane]);
+    const bool is_if = w == ST_IFI || w == ST_IFQ, is_aud = w == ST_AUD;
+    if (phase == 0) r.load(x, lane, is_if ? 0 : (is_aud ? 1 : 2), is_if ? w - ST_IFI : (is_aud ? 0 : w - ST_IMGI));
+    else if (phase == 1) r.step(x, lane, t);
     else r.save(x);
-  } else if (w == 11) {
+  } else if (w == ST_AGC) {
+    k.agc.resize(32); RoleAgc &r = k.agc[lane];
+    if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x);
+  } else if (w == ST_OUT) {
     k.out.resize(32); RoleOut &r = k.out[lane];
-    if (phase == 0) r.load(x, lane, oc, oa); else if (phase == 1) r.step_a(x, lane, t, oc, oa); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane, oc, oa);
+    if (phase == 0) r.load(x, lane); else if (phase == 1) r.step_a(x, lane, t); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane);
   } else if (ssb) {
-    if (w == 4) {
+    if (w == ST_NCO) {
       k.nco.resize(32); RoleNco &r = k.nco[lane];
       if (phase == 0) {
         r.load(x, lane);
@@ -82,43 +72,91 @@ void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
         else r.step(x, lane, t);
       } else r.save(x);
     }
-    else { k.hil.resize(32); RoleHilbert &r = k.hil[lane]; const int sub = w - 5;
+    else { k.hil.resize(32); RoleHilbert &r = k.hil[lane]; const int sub = w - ST_HIL0;
       if (phase == 0) r.load(x, lane, sub); else if (phase == 1) r.step(x, g_hilbert, lane, sub, t); else r.save(x, lane, sub); }
   } else {
-    if (w == 4) { k.pll.resize(32); RolePll &r = k.pll[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
-    else if (w == 5) { k.nco2.resize(32); RoleNco2 &r = k.nco2[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
-    else if (w == 8) { k.mag.resize(32); RoleMag &r = k.mag[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
-    else { k.bq.resize(32); RoleBiquad &r = k.bq[lane]; const int rail = w - 6;
-      if (phase == 0) r.load(x, lane, 2, rail);
-      else if (phase == 1) r.step(x.tile(E_Z2, (t % NZ2) * 2 + rail), x.tile(E_V, (t % NZ2) * 2 + rail), lane, r.cid >= 0 && env_flag(x, lane, t) != 0);
-      else r.save(x, 2, rail); }
+    if (w == ST_PLL) { k.pll.resize(32); RolePll &r = k.pll[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
+    else if (w == ST_NCO2) { k.nco2.resize(32); RoleNco2 &r = k.nco2[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
+    else { k.mag.resize(32); RoleMag &r = k.mag[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x); }
   }
 }
 
-void run_group(const SdrLaunch &L, const SdrGroup &G, bool reverse) {
-  std::vector<unsigned char> smem(SDR_SMEM_BYTES, 0xFF);
-  Ctx x; x.L = &L; x.G = &G; x.smem = smem.data(); x.gidx = 0; x.t0 = 0; x.prof = false;
-  for (int i = 0; i < 257; i++) x.f(S_SINE)[i] = L.tabs->sine[i];
-  for (int i = 0; i < 32; i++) reinterpret_cast<int *>(smem.data() + S_CID)[i] = G.cid[i];
+/* Scheduling policies (SDR_EMU_SCHED): the stages of a group only obey the hand-over rules of the launch's plan
+ * (SdrLay::deps), so every order those rules allow must give the same bits.
+ *   lockstep (default)  the lock-step schedule: at step s every stage with delay d runs tile s - d; the rules are asserted
+ *                       (SDR_EMU_REVERSE=1 reverses the order of the stages inside a step)
+ *   producers           always run the most upstream runnable stage: producers get as far ahead as the rules allow
+ *   consumers           always run the most downstream runnable stage: producers run only when somebody needs them
+ *   random:<seed>       a runnable stage picked at random
+ * Shared memory is poisoned before every group, so a tile read before it was written or after it was overwritten shows up. */
+static bool runnable(const SdrLay &Y, const std::vector<long long> &done, int s, uint32_t n) {
+  if (!Y.active[s] || done[s] >= (long long)n) return false;
+  const long long t = done[s];
+  for (int i = 0; i < SDR_MAX_DEPS && Y.deps[s][i].stage >= 0; i++) {
+    const SdrDep d = Y.deps[s][i];
+    const long long u = d.kind ? (t | (long long)(Y.tpb - 1)) : t + d.k;
+    if (u >= 0 && done[d.stage] <= u) return false;
+  }
+  return true;
+}
+
+int run_group(const SdrLaunch &L, const SdrGroup &G) {
+  const SdrLay &Y = L.lay;
+  std::vector<unsigned char> smem((size_t)Y.smem_bytes, 0xFF);
+  Ctx x; x.L = &L; x.Y = &L.lay; x.G = &G; x.smem = smem.data(); x.gidx = 0; x.t0 = 0; x.prof = false;
+  for (int i = 0; i < 257; i++) x.f(Y.o_sine)[i] = L.tabs->sine[i];
+  for (int i = 0; i < 32; i++) reinterpret_cast<int *>(smem.data() + Y.o_cid)[i] = G.cid[i];
   for (int i = 0; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i++) {
     const int id = G.lut_ids[i / SDR_AGC_LUT_STRIDE];
-    if (id >= 0) x.f(S_LUT)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
+    if (id >= 0) x.f(Y.o_lut)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
   }
-  const int cls = G.cls;
   const uint32_t n = L.n_tiles;
-  std::vector<Warp> W(SDR_WARPS);
-  for (int w = 0; w < SDR_WARPS; w++) for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 0, 0);
-  const int dmax = cls == CLS_SSB ? D_SSB_MAX : D_ENV_MAX;
-  for (uint32_t s = 0; s < n + (uint32_t)dmax; s++) {
-    for (int wi = 0; wi < SDR_WARPS; wi++) {
-      int w = reverse ? SDR_WARPS - 1 - wi : wi;
-      long long tau = (long long)s - delay_of(cls, w);
-      if (tau < 0 || tau >= (long long)n) continue;
-      for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 1, (uint32_t)tau);
-      for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 3, (uint32_t)tau);
+  std::vector<Warp> W(SDR_STAGES);
+  std::vector<long long> done(SDR_STAGES, 0);
+  std::vector<int> order; /* active stages, most upstream first */
+  for (int d = 0; d <= Y.dmax; d++) for (int s = 0; s < SDR_STAGES; s++) if (Y.active[s] && Y.delay[s] == d) order.push_back(s);
+  for (int s : order) for (int lane = 0; lane < 32; lane++) dispatch(x, W[s], s, lane, 0, 0);
+  auto run_tile = [&](int s) {
+    const uint32_t t = (uint32_t)done[s];
+    for (int lane = 0; lane < 32; lane++) dispatch(x, W[s], s, lane, 1, t);
+    for (int lane = 0; lane < 32; lane++) dispatch(x, W[s], s, lane, 3, t);
+    done[s]++;
+  };
+  const char *pol = getenv("SDR_EMU_SCHED");
+  std::string policy = pol && *pol ? pol : "lockstep";
+  if (policy == "lockstep") {
+    const char *r = getenv("SDR_EMU_REVERSE");
+    const bool reverse = r && r[0] == '1';
+    for (uint32_t s = 0; s < n + (uint32_t)Y.dmax; s++) {
+      /* all stages of a step see the state the previous step left: collect first, then run */
+      std::vector<int> now;
+      for (int st = 0; st < SDR_STAGES; st++) {
+        if (!Y.active[st]) continue;
+        const long long tau = (long long)s - Y.delay[st];
+        if (tau < 0 || tau >= (long long)n) continue;
+        if (done[st] != tau || !runnable(Y, done, st, n)) { fprintf(stderr, "[emu] lock-step schedule violates a hand-over rule: stage %d tile %lld\n", st, tau); return 1; }
+        now.push_back(st);
+      }
+      if (reverse) std::reverse(now.begin(), now.end());
+      for (int st : now) run_tile(st);
     }
+  } else {
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    if (policy.rfind("random", 0) == 0 && policy.size() > 7) rng ^= strtoull(policy.c_str() + 7, nullptr, 10) * 0xBF58476D1CE4E5B9ull;
+    for (;;) {
+      std::vector<int> can;
+      for (int st : order) if (runnable(Y, done, st, n)) can.push_back(st);
+      if (can.empty()) break;
+      int pick;
+      if (policy == "producers") pick = can.front();
+      else if (policy == "consumers") pick = can.back();
+      else { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; pick = can[(size_t)(rng % can.size())]; }
+      run_tile(pick);
+    }
+    for (int st : order) if (done[st] != (long long)n) { fprintf(stderr, "[emu] deadlock: stage %d stopped at tile %lld of %u\n", st, done[st], n); return 2; }
   }
-  for (int w = 0; w < SDR_WARPS; w++) for (int lane = 0; lane < 32; lane++) dispatch(x, W[w], w, lane, 2, 0);
+  for (int s : order) for (int lane = 0; lane < 32; lane++) dispatch(x, W[s], s, lane, 2, 0);
+  return 0;
 }
 
 }  // namespace
@@ -128,9 +166,8 @@ extern "C" {
 int sdrk_setup_device(const float *hilbert64) { memcpy(g_hilbert, hilbert64, sizeof g_hilbert); return 0; }
 
 int sdrk_launch_pipeline(const SdrLaunch *L, void *) {
-  const char *r = getenv("SDR_EMU_REVERSE");
-  bool reverse = r && r[0] == '1';
-  for (uint32_t g = 0; g < L->n_groups; g++) run_group(*L, L->groups[g], reverse);
+  if (lay_check(&L->lay)) return 100 + lay_check(&L->lay);
+  for (uint32_t g = 0; g < L->n_groups; g++) { int e = run_group(*L, L->groups[g]); if (e) return e; }
   return 0;
 }
 
