@@ -65,14 +65,13 @@ static inline void lay_rules(SdrLay *L) {
   lay_dep(L, ST_IN, x0, 0, -L->nr);
   if (nb) {
     /* blanker, C:606-650.  HBM ring planes: IN writes I/Q of block B into slot B % 3, whose previous content (block B - 3)
-     * NB-out fetched one block (tpb tiles) ago; ENVL does the same for the envelope plane, read by the scan up to the
-     * first tile of the previous block.  Mask slots in shared memory: NB-out reads the final mask of tile t once the scan
+     * NB-out fetched one block (tpb tiles) ago; ENVL does the same for the envelope plane, which the scan fetches for the last
+     * time with the first tile of the previous block.  Mask slots in shared memory: NB-out reads the final mask of tile t once the scan
      * of tile t is over; the scan recycles the oldest mask slot two tiles after NB-out has left it (see RoleNb). */
     lay_dep(L, ST_IN, ST_NBO, 0, -tpb);
-    lay_dep(L, ST_ENVL, ST_IN, 0, 0);
-    lay_dep(L, ST_ENVL, ST_NB, 0, -tpb);
-    lay_dep(L, ST_NB, ST_ENVL, 0, -2);   /* the envelopes the scan requests at the end of tile t (for tile t + 1) were written by ENVL(t - 2) at the latest */
-    lay_dep(L, ST_NB, ST_NBO, 0, -2);
+    lay_dep(L, ST_ENVL, ST_IN, 0, 0);    /* (and through it, IN(t) <- NB-out(t - tpb) <- NB(t - tpb): the scan has fetched the envelopes ENVL(t) replaces) */
+    lay_dep(L, ST_NB, ST_NBO, 0, -2);    /* (also covers the envelopes the scan requests at the end of tile t for tile t + 1: ENVL(t - 2) wrote
+                                            the latest of them, and NB-out(t - 2) has waited for ENVL(t - 2)) */
     lay_dep(L, ST_NBO, ST_NB, 0, 0);
     lay_dep(L, ST_NBO, ST_ENVL, 0, 0);   /* overwrites the slot ENVL reads */
     lay_dep(L, ST_IFI, ST_NBO, 0, 0);

@@ -15,10 +15,23 @@ import signals as S
 from test_oracle import GOLDEN, load_golden
 
 
-@pytest.mark.parametrize("reverse", ["0", "1"])
+SCHEDULES = ["lockstep", "lockstep-reversed", "producers", "consumers", "random:1", "random:2/late", "producers/late"]
+
+
+def set_schedule(monkeypatch, sched):
+    """The stages of a group only obey the hand-over rules of the launch's plan (sdr_lay.h): every order those rules allow
+    must give the same bits.  tests/emu runs them in lock step (stage order inside a step either way), with producers as
+    far ahead as the rules allow, with consumers first, and in random order."""
+    sched, _, landing = sched.partition("/")
+    monkeypatch.setenv("SDR_EMU_ASYNC", landing or "early")  # asynchronous copies land at the request, or as late as their wait
+    monkeypatch.setenv("SDR_EMU_REVERSE", "1" if sched == "lockstep-reversed" else "0")
+    monkeypatch.setenv("SDR_EMU_SCHED", "lockstep" if sched.startswith("lockstep") else sched)
+
+
+@pytest.mark.parametrize("sched", SCHEDULES)
 @pytest.mark.parametrize("cfg,nch,nblk", [(1, 1, 40), (2, 40, 30), (3, 6, 30), (4, 70, 24), (5, 5, 30)])
-def test_emulated_pipeline_matches_oracle(oracle, emu_lib, monkeypatch, cfg, nch, nblk, reverse):
-    monkeypatch.setenv("SDR_EMU_REVERSE", reverse)  # warp order inside a step must not matter
+def test_emulated_pipeline_matches_oracle(oracle, emu_lib, monkeypatch, cfg, nch, nblk, sched):
+    set_schedule(monkeypatch, sched)
     I, Q, ev = S.make(cfg, list(range(nch)), nblk)
     o = oracle.run(I, Q, ev, threads=4)
     a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(7, 1, 13), return_batch=True)
@@ -144,3 +157,38 @@ def test_emulated_lone_mode_switch(oracle, emu_lib):
     a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(30,), return_batch=True)
     assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
     assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+
+
+def test_every_hand_over_rule_is_needed(oracle, emu_lib, monkeypatch):
+    """Mutation check of the test scaffold itself: leaving out ANY single hand-over rule of the plans (sdr_lay.h) must be
+    noticed by at least one schedule -- as wrong bits (shared memory is poisoned, a ring slot read too early or
+    overwritten too early changes the output), a violated lock-step assertion or a stall.  Otherwise a forgotten rule in
+    the kernel could hide behind the schedules tried here."""
+    import audiosdr_b200 as A
+    cases = []
+    for cfg, nch, nblk in [(2, 40, 30), (4, 70, 24)]:
+        I, Q, ev = S.make(cfg, list(range(nch)), nblk)
+        cases.append((I, Q, ev, oracle.run(I, Q, ev, threads=4)["audio"]))
+
+    def noticed():
+        for sched, landing in (("producers", "early"), ("consumers", "early"), ("random:1", "late"), ("producers", "late")):
+            monkeypatch.setenv("SDR_EMU_SCHED", sched)
+            monkeypatch.setenv("SDR_EMU_ASYNC", landing)  # asynchronous copies land at the request / as late as their wait
+            for I, Q, ev, want in cases:
+                try:
+                    got = harness.run_batch(emu_lib, I, Q, ev, chunks=(7, 1, 13))
+                except A.SdrError:
+                    return True
+                if not harness.bits_equal(got, want):
+                    return True
+        return False
+
+    monkeypatch.setenv("SDR_EMU_DROP_RULE", "-1")
+    assert not noticed()  # all rules in place: every schedule is exact
+    missed = []
+    for rule in range(30):
+        monkeypatch.setenv("SDR_EMU_DROP_RULE", str(rule))
+        if not noticed():
+            missed.append(rule)
+    # rule numbers beyond a plan's rule count drop nothing; the longest plan (ENV class with blanker) has 29 rules
+    assert [r for r in missed if r < 25] == [], "schedules did not notice the missing rule(s) %s" % missed
