@@ -55,7 +55,8 @@ class ChannelStatus(C.Structure):
 
 
 def lib_path():
-    return os.path.join(HERE, "libsdr_batch.so")
+    """audiosdr_b200/libsdr_batch.so; SDR_LIB names another build of the same sources for A/B experiments (tools/build_variants.py)."""
+    return os.environ.get("SDR_LIB") or os.path.join(HERE, "libsdr_batch.so")
 
 
 def _bind(L):

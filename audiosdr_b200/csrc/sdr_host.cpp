@@ -627,6 +627,17 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
     L.lay = b.lay; L.groups = h->d_groups + b.first; L.n_groups = b.count;
     L.n_tiles = n_blocks * (uint32_t)b.lay.tpb;
     L.prof = h->prof_on ? h->d_prof + (size_t)b.first * SDR_PROF_SLOTS : nullptr;
+    if (getenv("SDR_DEBUG_PLAN")) {
+      static int shown = 0;
+      if (shown++ < 8)
+#ifndef SDR_EMU
+        fprintf(stderr, "[sdr] launch: class %d feat %u T %d warps %d smem %d B groups %u -> %d CTA(s)/SM; rings nr %d na %d nc %d ni %d hq %d nz %d nz2 %d, input depth %d\n",
+                b.lay.cls, b.lay.feat, b.lay.T, b.lay.n_warps, b.lay.smem_bytes, b.count, sdrk_occupancy(&L), b.lay.nr, b.lay.na, b.lay.nc, b.lay.ni,
+                b.lay.hq_tiles, b.lay.nz, b.lay.nz2, b.lay.in_depth);
+#else
+        fprintf(stderr, "[sdr] launch: class %d feat %u T %d warps %d smem %d B groups %u\n", b.lay.cls, b.lay.feat, b.lay.T, b.lay.n_warps, b.lay.smem_bytes, b.count);
+#endif
+    }
     int e = sdrk_launch_pipeline(&L, s);
     if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
     h->launches++;

@@ -41,12 +41,18 @@ static inline int lay_align(int v, int a) { return (v + a - 1) / a * a; }
 /* test scaffold only (tests/emu): SDR_EMU_DROP_RULE=n leaves out the n-th rule of every plan, to show that the
  * adversarial schedules of the emulation notice a missing rule */
 static int lay_emu_rule_counter = 0;
+static int lay_emu_dropped[4] = {-1, -1, -1, -1}; /* stage, barrier owner, kind, k of the rule left out */
 #endif
 
 static inline void lay_dep(SdrLay *L, int stage, int on, int kind, int k) {
   if (!L->active[on] || !L->active[stage]) return;
+  on = L->bar_of[on];
+  for (int i = 0; i < SDR_MAX_DEPS; i++) /* the members of a barrier group add the same rule once */
+    if (L->deps[stage][i].stage == on && L->deps[stage][i].kind == kind && L->deps[stage][i].k == k) return;
 #ifdef SDR_EMU
-  { const char *e = getenv("SDR_EMU_DROP_RULE"); if (e && *e && atoi(e) == lay_emu_rule_counter++) return; }
+  if (lay_emu_dropped[0] == stage && lay_emu_dropped[1] == on && lay_emu_dropped[2] == kind && lay_emu_dropped[3] == k) return;
+  { const char *e = getenv("SDR_EMU_DROP_RULE");
+    if (e && *e && atoi(e) == lay_emu_rule_counter++) { lay_emu_dropped[0] = stage; lay_emu_dropped[1] = on; lay_emu_dropped[2] = kind; lay_emu_dropped[3] = k; return; } }
 #endif
   for (int i = 0; i < SDR_MAX_DEPS; i++)
     if (L->deps[stage][i].stage < 0) { L->deps[stage][i].stage = (int8_t)on; L->deps[stage][i].kind = (int8_t)kind; L->deps[stage][i].k = (int16_t)k; return; }
@@ -56,7 +62,7 @@ static inline void lay_dep(SdrLay *L, int stage, int on, int kind, int k) {
 /* The rule set as ring depths stand in *L (called by lay_build after the depths are final). */
 static inline void lay_rules(SdrLay *L) {
 #ifdef SDR_EMU
-  lay_emu_rule_counter = 0;
+  lay_emu_rule_counter = 0; lay_emu_dropped[0] = -1;
 #endif
   for (int s = 0; s < SDR_STAGES; s++) for (int i = 0; i < SDR_MAX_DEPS; i++) { L->deps[s][i].stage = -1; L->deps[s][i].kind = 0; L->deps[s][i].k = 0; }
   const int nb = (L->feat & LF_NB) != 0, tpb = L->tpb;
@@ -161,6 +167,11 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   }
   L->active[ST_AUD] = L->active[ST_AGC] = L->active[ST_OUT] = 1; d[ST_OUT] = (int8_t)(d[ST_AGC] + 1);
   for (int s = 0; s < SDR_STAGES; s++) if (L->active[s] && d[s] > L->dmax) L->dmax = d[s];
+  /* barrier groups */
+  for (int s = 0; s < 16; s++) { L->bar_of[s] = (uint8_t)s; L->bar_count[s] = 1; }
+  L->bar_of[ST_IFQ] = ST_IFI; L->bar_count[ST_IFI] = 2;
+  if (cls == CLS_SSB) { for (int h = 1; h < L->n_hil; h++) L->bar_of[ST_HIL0 + h] = ST_HIL0; L->bar_count[ST_HIL0] = (uint8_t)L->n_hil; }
+  else { L->bar_of[ST_IMGQ] = ST_IMGI; L->bar_count[ST_IMGI] = 2; }
   /* minimum ring depths: a tile's slot lives from the writer's step to the last reader's step */
   const int x0 = cls == CLS_SSB ? ST_NCO : ST_PLL;
   const int back_q = (255 + T - 1) / T, back_c = als ? tpb : 0;
@@ -179,7 +190,8 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   if (nb) { L->o_nbs = o; o += 32 * SDR_LANES * 16; L->o_mask = o; o += 3 * 128 * SDR_LANES; }
   if (als) { L->o_alsc = o; o += 128 * SDR_LANES * 4; }
   L->ins_row = T + 4; /* staging rows padded by 16 bytes: a lane reading its own row with 16-byte loads is bank-conflict free */
-  L->o_ins = o; o += 2 * SDR_LANES * L->ins_row * 4;
+  L->in_depth = T == 32 ? 1 : (T == 16 ? 2 : 4); /* the request has to cover the DRAM latency: about one 32-sample tile time */
+  L->o_ins = o; o += L->in_depth * 2 * SDR_LANES * L->ins_row * 4;
   L->o_outs = o; o += SDR_LANES * L->ins_row * 4;
   const int fixed = o;
   /* rings: grow round robin while the budget allows */

@@ -17,7 +17,7 @@
 #define SDR_TMAX 32     /* longest pipeline tile in samples (a launch's tile length is SdrLay::T: 32, 16 or 8; 128 / T tiles = one reference block) */
 #define SDR_STAGES 14   /* pipeline stage ids (sdr_lay.h); a launch runs the subset its bucket needs, one warp each */
 #define SDR_BAR_W 32    /* hand-over barriers per stage: stage s signals tile t on barrier (s, t % SDR_BAR_W) */
-#define SDR_MAX_DEPS 6  /* hand-over rules per stage */
+#define SDR_MAX_DEPS 4  /* hand-over rules per stage */
 #define SDR_HQ_MIRROR 7 /* rows of the Hilbert Q ring repeated behind its end (sdr_pipeline.cuh, hq_at) */
 
 /* ---- per-channel state words (reference member it stands for) ---- */
@@ -102,7 +102,7 @@ typedef struct {
 
 /* ---- one hand-over rule: before tile t a stage waits until stage `stage` has finished tile t + k (kind 0) or the last tile
  * of t's block, t | (tpb - 1) (kind 1); tiles below 0 never block.  Built by lay_build() (sdr_lay.h). */
-typedef struct { int8_t stage, kind; int16_t k; } SdrDep;
+typedef struct { int8_t stage, kind; int16_t k; } SdrDep; /* `stage`: a barrier owner, SdrLay::bar_of */
 
 /* ---- shared-memory plan + hand-over rules of one launch (one bucket = pipeline class x optional stages), sdr_lay.h ---- */
 typedef struct {
@@ -116,6 +116,10 @@ typedef struct {
   int32_t smem_bytes, n_warps, dmax, error;
   uint8_t stage_of_warp[16];         /* physical warp -> stage id */
   uint8_t active[16];                /* stage id -> runs in this launch */
+  uint8_t bar_of[16];                /* stage id -> the stage whose barriers it signals: stages that always hand over together (the two IF rails,
+                                        the Hilbert warps, the two image rails) share one barrier per tile, completed by all their arrivals */
+  uint8_t bar_count[16];             /* arrivals that complete a barrier of that stage id */
+  int32_t in_depth;                  /* input tiles requested ahead (landing buffers of the IN stage) */
   int8_t delay[16];                  /* the stage's delay in the lock-step schedule (documentation, deadlock-freedom proof, emulation) */
   SdrDep deps[SDR_STAGES][SDR_MAX_DEPS];
 } SdrLay;

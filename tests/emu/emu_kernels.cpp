@@ -36,6 +36,7 @@ struct Warp {
  * parts, the kernel separates them with __syncwarp()), 2 = save -- mirrors run_stage() of sdr_kernel.cu */
 void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
   if (phase == 3 && w != ST_IN && w != ST_OUT) return;
+  x.k.set(*x.Y, phase == 0 ? 0u : (phase == 2 ? x.L->n_tiles : t)); /* the kernel's tile loop counts these */
   const bool ssb = x.Y->cls == CLS_SSB;
   if (w == ST_IN) { k.in.resize(32); RoleIn &r = k.in[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step_a(x, lane, t); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane); }
   else if (w == ST_NB) { k.nbk.resize(32); RoleNb &r = k.nbk[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }
@@ -95,7 +96,9 @@ static bool runnable(const SdrLay &Y, const std::vector<long long> &done, int s,
   for (int i = 0; i < SDR_MAX_DEPS && Y.deps[s][i].stage >= 0; i++) {
     const SdrDep d = Y.deps[s][i];
     const long long u = d.kind ? (t | (long long)(Y.tpb - 1)) : t + d.k;
-    if (u >= 0 && done[d.stage] <= u) return false;
+    if (u < 0) continue;
+    for (int m = 0; m < SDR_STAGES; m++) /* a barrier completes when every stage of its group has arrived */
+      if (Y.active[m] && Y.bar_of[m] == d.stage && done[m] <= u) return false;
   }
   return true;
 }
