@@ -34,6 +34,37 @@ enum {
 /* bucket features */
 enum { LF_NB = 1u, LF_ALS = 2u };
 
+/* The plan of every 32-sample-tile launch is the same (whatever optional stages the bucket has): offsets and ring depths
+ * are compile-time constants of the 32-sample kernel, and a group with all stages fills the SM's shared memory. */
+enum {
+  LAY32_NR = 5, LAY32_NI = 6, LAY32_HQ_TILES = 12, LAY32_NA_SSB = 3, LAY32_NA_ENV = 5, LAY32_NC = 6, LAY32_NZ = 5, LAY32_NZ2 = 3,
+  LAY32_TILE = 32 * SDR_LANES * 4,
+  LAY32_SINE = 0, LAY32_LUT = 1152, LAY32_NCOT = 3328, LAY32_CID = 3584, LAY32_BAR = 3712,
+  LAY32_NBS = LAY32_BAR + SDR_STAGES * SDR_BAR_W * 8,
+  LAY32_INS = LAY32_NBS + 32 * SDR_LANES * 16,
+  LAY32_OUTS = LAY32_INS + 2 * SDR_LANES * 36 * 4,
+  LAY32_R = LAY32_OUTS + SDR_LANES * 36 * 4,
+  LAY32_CLASS = LAY32_R + LAY32_NR * 2 * LAY32_TILE,
+  /* SSB */
+  LAY32_HQ = LAY32_CLASS,
+  LAY32_HI = LAY32_HQ + (LAY32_HQ_TILES * 16 + SDR_HQ_MIRROR) * SDR_LANES * 8,
+  LAY32_SA = LAY32_HI + LAY32_NI * LAY32_TILE,
+  LAY32_SC = LAY32_SA + LAY32_NA_SSB * LAY32_TILE,
+  LAY32_SMASK = LAY32_SC + LAY32_NC * LAY32_TILE,
+  LAY32_SALSC = LAY32_SMASK + 3 * 128 * SDR_LANES,
+  LAY32_SSB_END = LAY32_SALSC + 128 * SDR_LANES * 4,
+  /* ENV */
+  LAY32_Z = LAY32_CLASS,
+  LAY32_Z2 = LAY32_Z + LAY32_NZ * 2 * LAY32_TILE,
+  LAY32_EA = LAY32_Z2 + LAY32_NZ2 * 2 * LAY32_TILE,
+  LAY32_EC = LAY32_EA + LAY32_NA_ENV * LAY32_TILE,
+  LAY32_EMASK = LAY32_EC + LAY32_NC * LAY32_TILE,
+  LAY32_EALSC = LAY32_EMASK + 3 * 128 * SDR_LANES,
+  LAY32_FLAGS = LAY32_EALSC + 128 * SDR_LANES * 4,
+  LAY32_CARR = LAY32_FLAGS + 8 * SDR_LANES * 4,
+  LAY32_ENV_END = LAY32_CARR + 8 * SDR_LANES * 4
+};
+
 static inline int lay_align(int v, int a) { return (v + a - 1) / a * a; }
 
 #ifdef SDR_EMU
@@ -78,7 +109,7 @@ static inline void lay_rules(SdrLay *L) {
     lay_dep(L, ST_ENVL, ST_IN, 0, 0);    /* (and through it, IN(t) <- NB-out(t - tpb) <- NB(t - tpb): the scan has fetched the envelopes ENVL(t) replaces) */
     lay_dep(L, ST_NB, ST_NBO, 0, -2);    /* (also covers the envelopes the scan requests at the end of tile t for tile t + 1: ENVL(t - 2) wrote
                                             the latest of them, and NB-out(t - 2) has waited for ENVL(t - 2)) */
-    lay_dep(L, ST_NBO, ST_NB, 0, 0);
+    lay_dep(L, ST_NBO, ST_NB, 0, -1);    /* the mask words NB-out(t) reads were last touched by the scan of tile t - 1 (windows and edges reach back into the oldest block, see RoleNb) */
     lay_dep(L, ST_NBO, ST_ENVL, 0, 0);   /* overwrites the slot ENVL reads */
     lay_dep(L, ST_IFI, ST_NBO, 0, 0);
     lay_dep(L, ST_IFQ, ST_NBO, 0, 0);
@@ -172,6 +203,28 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   L->bar_of[ST_IFQ] = ST_IFI; L->bar_count[ST_IFI] = 2;
   if (cls == CLS_SSB) { for (int h = 1; h < L->n_hil; h++) L->bar_of[ST_HIL0 + h] = ST_HIL0; L->bar_count[ST_HIL0] = (uint8_t)L->n_hil; }
   else { L->bar_of[ST_IMGQ] = ST_IMGI; L->bar_count[ST_IMGI] = 2; }
+  if (T == 32) {
+    /* the fixed plan (LAY32_*): lock-step delays as if every optional stage existed, so that the ring depths are the same
+     * for every bucket */
+    d[ST_IN] = 0; d[ST_ENVL] = 1; d[ST_NB] = 1; d[ST_NBO] = 2; d[ST_IFI] = d[ST_IFQ] = 3;
+    if (cls == CLS_SSB) { d[ST_NCO] = 4; for (int h = 0; h < 4; h++) d[ST_HIL0 + h] = 5; d[ST_AUD] = 6; d[ST_AGC] = 7; d[ST_OUT] = 8; }
+    else { d[ST_PLL] = 4; d[ST_NCO2] = 8; d[ST_IMGI] = d[ST_IMGQ] = 9; d[ST_MAG] = 10; d[ST_AUD] = 11; d[ST_AGC] = 14; d[ST_OUT] = 15; }
+    L->dmax = d[ST_OUT];
+    L->nr = LAY32_NR; L->nc = LAY32_NC; L->ins_row = 36; L->in_depth = 1;
+    L->o_sine = LAY32_SINE; L->o_lut = LAY32_LUT; L->o_ncot = LAY32_NCOT; L->o_cid = LAY32_CID; L->o_bar = LAY32_BAR; L->o_nbs = LAY32_NBS;
+    L->o_ins = LAY32_INS; L->o_outs = LAY32_OUTS; L->o_r = LAY32_R;
+    if (cls == CLS_SSB) {
+      L->ni = LAY32_NI; L->hq_tiles = LAY32_HQ_TILES; L->hq_rows = LAY32_HQ_TILES * 16; L->na = LAY32_NA_SSB;
+      L->o_hq = LAY32_HQ; L->o_hi = LAY32_HI; L->o_a = LAY32_SA; L->o_c = LAY32_SC; L->o_mask = LAY32_SMASK; L->o_alsc = LAY32_SALSC;
+      L->smem_bytes = als ? LAY32_SSB_END : (nb ? LAY32_SALSC : LAY32_SMASK);
+    } else {
+      L->nz = LAY32_NZ; L->nz2 = LAY32_NZ2; L->na = LAY32_NA_ENV;
+      L->o_z = LAY32_Z; L->o_z2 = LAY32_Z2; L->o_a = LAY32_EA; L->o_c = LAY32_EC; L->o_mask = LAY32_EMASK; L->o_alsc = LAY32_EALSC;
+      L->o_flags = LAY32_FLAGS; L->o_carr = LAY32_CARR;
+      L->smem_bytes = LAY32_ENV_END;
+    }
+    (void)budget; (void)max_slack;
+  } else {
   /* minimum ring depths: a tile's slot lives from the writer's step to the last reader's step */
   const int x0 = cls == CLS_SSB ? ST_NCO : ST_PLL;
   const int back_q = (255 + T - 1) / T, back_c = als ? tpb : 0;
@@ -223,6 +276,7 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   L->o_a = o; o += L->na * tile_b;
   L->o_c = o; o += L->nc * tile_b;
   L->smem_bytes = o;
+  }
   /* warps: one per active stage, in stage order until a measured placement is supplied (lay_place) */
   L->n_warps = 0;
   for (int s = 0; s < SDR_STAGES; s++) if (L->active[s]) L->stage_of_warp[L->n_warps++] = (uint8_t)s;

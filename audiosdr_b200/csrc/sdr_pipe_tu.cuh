@@ -74,7 +74,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
 #pragma unroll 1
   for (uint32_t s = 0; s < steps; s++) {
     const long long tau = (long long)s - delay;
-    if (tau >= 0 && tau < (long long)n) { body((uint32_t)tau); x.k.advance(*x.Y); }
+    if (tau >= 0 && tau < (long long)n) { body((uint32_t)tau); x.k.advance(x); }
     cta_barrier();
   }
 }
@@ -85,7 +85,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
   const long long t_loaded = prof ? clock64() : 0;
   cta_barrier(); /* histories and tables are in shared memory */
   const uint32_t n = x.L->n_tiles, tpbm = (uint32_t)(x.tpb() - 1);
-  const uint32_t bars = (uint32_t)__cvta_generic_to_shared(x.smem + x.Y->o_bar);
+  const uint32_t bars = (uint32_t)__cvta_generic_to_shared(x.smem + x.o_bar());
   const bool skip = prof && ((x.L->diag_skip >> stage) & 1u);
   const uint32_t my_bar = bars + (uint32_t)x.Y->bar_of[stage] * (SDR_BAR_W * 8u);
   long long busy = 0, waiting = 0;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
     if (!skip) body(t);
     __syncwarp();
     if ((threadIdx.x & 31) == 0) bar_arrive(my_bar + (t & (SDR_BAR_W - 1)) * 8u);
-    x.k.advance(*x.Y);
+    x.k.advance(x);
     if (prof) { const long long t1 = clock64(); waiting += t0 - tw; busy += t1 - t0; }
   }
   if (prof && (threadIdx.x & 31) == 0) {
@@ -197,17 +197,17 @@ __device__ __forceinline__ void pipeline_cta(const SdrLaunch &L, unsigned char *
   x.prof = PROF;
   x.t0 = PROF ? clock64() : 0;
   const int nthr = (int)blockDim.x;
-  for (int i = threadIdx.x; i < 257; i += nthr) x.f(x.Y->o_sine)[i] = L.tabs->sine[i];
-  if (threadIdx.x < SDR_LANES) reinterpret_cast<int *>(smem + x.Y->o_cid)[threadIdx.x] = x.G->cid[threadIdx.x];
+  for (int i = threadIdx.x; i < 257; i += nthr) x.f(x.o_sine())[i] = L.tabs->sine[i];
+  if (threadIdx.x < SDR_LANES) reinterpret_cast<int *>(smem + x.o_cid())[threadIdx.x] = x.G->cid[threadIdx.x];
   {
-    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem + x.Y->o_bar);
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem + x.o_bar());
     for (int i = threadIdx.x; i < SDR_STAGES * SDR_BAR_W; i += nthr) bar_init(bars + 8u * (uint32_t)i, (uint32_t)x.Y->bar_count[i / SDR_BAR_W]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads(); /* stage IN requests its first tile from load(), which needs the channel ids */
   for (int i = threadIdx.x; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i += nthr) { /* the group's AGC tables */
     const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];
-    if (id >= 0) x.f(x.Y->o_lut)[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
+    if (id >= 0) x.f(x.o_lut())[i] = L.agc_luts[(size_t)id * SDR_AGC_LUT_STRIDE + i % SDR_AGC_LUT_STRIDE];
   }
   /* Physical warp -> stage (SdrLay::stage_of_warp).  The warp scheduler of an SM sub-partition favours the HIGHER warp id
    * among eligible warps, and warp id % 4 picks the sub-partition, so the placement decides which stages compete for one

@@ -37,6 +37,7 @@ struct Warp {
 void dispatch(const Ctx &x, Warp &k, int w, int lane, int phase, uint32_t t) {
   if (phase == 3 && w != ST_IN && w != ST_OUT) return;
   x.k.set(*x.Y, phase == 0 ? 0u : (phase == 2 ? x.L->n_tiles : t)); /* the kernel's tile loop counts these */
+  emu_async_owner() = w; /* asynchronous copies belong to the stage (warp) that issued them: its lanes wait for their own, then meet at a warp barrier */
   const bool ssb = x.Y->cls == CLS_SSB;
   if (w == ST_IN) { k.in.resize(32); RoleIn &r = k.in[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step_a(x, lane, t); else if (phase == 3) r.step_b(x, lane, t); else r.save(x, lane); }
   else if (w == ST_NB) { k.nbk.resize(32); RoleNb &r = k.nbk[lane]; if (phase == 0) r.load(x, lane); else if (phase == 1) r.step(x, lane, t); else r.save(x, lane); }

@@ -170,3 +170,31 @@ def sample_channels(config, n_total, n_want, n_shards=8):
     while len(picks) < min(n_want, n_total):
         picks.add(splitmix64(c + 77 * config) % n_total); c += 1
     return sorted(picks)
+
+
+def sam_lock_unlock_case(n_channels, n_blocks, seed=3):
+    """SAM channels driven through lock -> out of lock -> envelope fallback -> re-lock (C:130-143, C:738-747).
+    The carrier sits near 6 890 Hz, jumps by +1.5 kHz (outside the lock detector's 5 890..7 890 Hz window) for the second
+    fifth of the run, comes back, disappears (noise only) for the fourth fifth and returns.  Returns (I, Q, events)."""
+    ns = n_blocks * N_BLOCK
+    t = np.arange(ns, dtype=np.float64)
+    w = 2.0 * np.pi / FS
+    seg = ns // 5
+    I = np.empty((n_channels, ns), np.int16); Q = np.empty_like(I)
+    ev = []
+    for c in range(n_channels):
+        df = 100.0 * _unit(chash(3, c, 4 + seed)) - 50.0
+        f = np.full(ns, 6890.0 + df)
+        f[seg:2 * seg] += 1500.0 + 20.0 * c
+        amp = np.full(ns, 0.3)
+        amp[3 * seg:4 * seg] = 0.0
+        ph = np.cumsum(w * f)
+        x = amp * (1.0 + 0.5 * np.cos(w * 1000.0 * t)) * np.exp(1j * ph)
+        rng = np.random.Generator(np.random.Philox(key=[0x5A3 + seed, c]))
+        noise = rng.standard_normal(2 * ns)
+        x = x + 0.01 * (noise[0::2] + 1j * noise[1::2])
+        I[c], Q[c] = quantise(x)
+        ev += channel_events(3, c, c)
+        if c % 3 == 1:  # some channels with the blanker on as well (the general ENV launch instead of the lean one)
+            ev += [(c, 0, "enableNoiseBlanker"), (c, 0, "setNoiseBlankerThresholdDb", 10.0)]
+    return I, Q, ev

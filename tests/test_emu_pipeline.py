@@ -171,7 +171,7 @@ def test_every_hand_over_rule_is_needed(oracle, emu_lib, monkeypatch):
         cases.append((I, Q, ev, oracle.run(I, Q, ev, threads=4)["audio"]))
 
     def noticed():
-        for sched, landing in (("producers", "early"), ("consumers", "early"), ("random:1", "late"), ("producers", "late")):
+        for sched, landing in (("producers", "early"), ("consumers", "early"), ("random:1", "late"), ("producers", "late"), ("random:6", "early")):
             monkeypatch.setenv("SDR_EMU_SCHED", sched)
             monkeypatch.setenv("SDR_EMU_ASYNC", landing)  # asynchronous copies land at the request / as late as their wait
             for I, Q, ev, want in cases:
@@ -192,3 +192,20 @@ def test_every_hand_over_rule_is_needed(oracle, emu_lib, monkeypatch):
             missed.append(rule)
     # rule numbers beyond a plan's rule count drop nothing; the shortest plan of these cases (ENV class with blanker) has 21 rules
     assert [r for r in missed if r < 21] == [], "schedules did not notice the missing rule(s) %s" % missed
+
+
+def test_emulated_sam_driven_out_of_lock_and_back(oracle, emu_lib, monkeypatch):
+    """SAM channels pushed out of the lock window and back (envelope fallback toggling per block, C:130-143), lean and
+    blanker-carrying ENV plans, under an adversarial schedule."""
+    set_schedule(monkeypatch, "random:4/late")
+    nch, nblk = 6, 400
+    I, Q, ev = S.sam_lock_unlock_case(nch, nblk)
+    o = oracle.run(I, Q, ev, threads=4)
+    col = harness.STATUS_FIELDS.index("sam_locked")
+    seg = nblk // 5
+    before = oracle.run(I[:, :(seg - 2) * 128], Q[:, :(seg - 2) * 128], ev, threads=4, want_pcm=False)["status"][:, col]
+    during = oracle.run(I[:, :(2 * seg - 2) * 128], Q[:, :(2 * seg - 2) * 128], ev, threads=4, want_pcm=False)["status"][:, col]
+    assert before.all() and not during.any()  # the case does what it says
+    a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(37, 1, 90), return_batch=True)
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
