@@ -28,7 +28,8 @@ SETTERS = dict(
 
 EXPORTS = ["sdr_batch_create", "sdr_batch_destroy", "sdr_batch_set", "sdr_batch_configure", "sdr_batch_process_device",
            "sdr_batch_process_host", "sdr_batch_get_status", "sdr_batch_get_agc_lookup", "sdr_batch_peek_state",
-           "sdr_batch_get_role_profile", "sdr_batch_launch_count", "sdr_batch_last_error", "sdr_batch_version"]
+           "sdr_batch_get_role_profile", "sdr_batch_launch_count", "sdr_batch_last_error", "sdr_batch_version",
+           "sdr_batch_process", "sdr_batch_state_bytes", "sdr_batch_export_state", "sdr_batch_import_state"]
 
 
 class SdrError(RuntimeError):
@@ -72,6 +73,10 @@ def _bind(L):
     L.sdr_batch_get_status.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_get_agc_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_peek_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+    L.sdr_batch_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.sdr_batch_state_bytes.restype = C.c_size_t
+    L.sdr_batch_export_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.sdr_batch_import_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_get_role_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sdr_batch_launch_count.argtypes = [C.c_void_p]
     L.sdr_batch_launch_count.restype = C.c_uint64
@@ -208,6 +213,25 @@ class SdrBatch:
         v = C.c_float()
         self._check(self.L.sdr_batch_peek_state(self.h, int(channel), int(word), C.byref(v)))
         return v.value
+
+    # ---- checkpoint / migration
+    def export_state(self, channels=None):
+        """Opaque per-channel blobs (uint8 array [n, sdr_batch_state_bytes()]): configuration + carry-over state."""
+        ids, n = self._ids(channels)
+        if ids is None:
+            n = self.n_channels
+        out = np.zeros((n, int(self.L.sdr_batch_state_bytes())), np.uint8)
+        self._check(self.L.sdr_batch_export_state(self.h, ids.ctypes.data if ids is not None else None, n, out.ctypes.data))
+        return out
+
+    def import_state(self, channels, blobs):
+        """Installs blobs from export_state (of any handle of the same library version) into the given channels."""
+        ids, n = self._ids(channels)
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
+        if ids is None:
+            n = self.n_channels
+        assert blobs.shape == (n, int(self.L.sdr_batch_state_bytes()))
+        self._check(self.L.sdr_batch_import_state(self.h, ids.ctypes.data if ids is not None else None, n, blobs.ctypes.data))
 
     def role_profile(self):
         """Per-stage busy fraction of the pipeline kernel (needs SDR_ROLE_PROFILE=1 at construction)."""

@@ -306,18 +306,21 @@ int env_int(const char *name, int dflt) { const char *e = getenv(name); return e
  * when a launch has more groups than SMs the plan trades ring slack for co-residency: shorter tiles shrink every ring
  * that is sized in tiles.  (SDR_TILE_SSB / SDR_TILE_ENV / SDR_CTAS_PER_SM / SDR_SLACK override the choice for experiments.) */
 int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
-  (void)n_sm;
+  /* Measured: the SSB class is bound by its four Hilbert warps per SM whatever the tile length, so it
+   * stays on the 32-sample plan; an ENV group is bound by the latency of its one PLL warp, so ENV buckets without blanker
+   * and ALS run 16-sample tiles in half the shared memory, two groups per SM -- when there are enough groups to share. */
   int T = 32, ctas = 1;
+  if (cls == CLS_ENV && !(feat & (LF_NB | LF_ALS)) && b.count > (uint32_t)n_sm) { T = 16; ctas = 2; }
   const int t_env = env_int(cls == CLS_SSB ? "SDR_TILE_SSB" : "SDR_TILE_ENV", 0);
-  if (t_env && !(feat & (LF_NB | LF_ALS))) T = t_env;
+  if (t_env && !(feat & (LF_NB | LF_ALS))) { T = t_env; ctas = T == 32 ? 1 : 2; }
   const int c_env = env_int("SDR_CTAS_PER_SM", 0);
   if (c_env > 0) ctas = c_env;
-  const int slack = env_int("SDR_SLACK", 2);
+  const int slack = env_int("SDR_SLACK", 0); /* extra ring slots only matter to the hand-over build (-DSDR_HANDOVER) */
   const int budget = (233472 - 1024 * ctas) / ctas; /* an SM has 228 KB, each resident CTA costs 1 KB of it */
   int rc = lay_build(&b.lay, cls, feat, T, budget > 232448 ? 232448 : budget, slack);
   if (rc) rc = lay_build(&b.lay, cls, feat, 32, 232448, 0);
   if (rc) return rc;
-  /* measured placements exist for the launches that run all 14 stages */
+  /* measured placements exist for the 14-warp launches */
   if (b.lay.n_warps == SDR_STAGES) {
     unsigned long long m = cls == CLS_SSB ? SDR_MAP_SSB_DEFAULT : SDR_MAP_ENV_DEFAULT;
     if (const char *e = getenv(cls == CLS_SSB ? "SDR_MAP_SSB" : "SDR_MAP_ENV")) m = strtoull(e, nullptr, 16);
@@ -648,6 +651,11 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
   return SDR_OK;
 }
 
+int sdr_batch_process(sdr_batch_t *h, const float *I, const float *Q, float *audio, uint32_t n_blocks, void *cuda_stream) {
+  const size_t pitch = (size_t)n_blocks * SDR_BLOCK_SAMPLES; /* densely packed float32 rows */
+  return sdr_batch_process_device(h, I, Q, pitch, SDR_FMT_F32, audio, pitch, SDR_FMT_F32, n_blocks, cuda_stream);
+}
+
 int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio,
                            size_t out_pitch, int out_fmt, uint32_t n_blocks) {
   if (!h || !I || !Q || !audio) return fail(SDR_ERR_ARG, "process_host: bad arguments");
@@ -691,6 +699,10 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
   /* work queued by an earlier process_device call on another stream must finish before the state is touched here */
   if (h->last_stream != h->s_comp && dev_sync(h->last_stream)) return SDR_ERR_CUDA;
   uint32_t done = 0, k = 0;
+  int err = 0;
+  /* on any failure the loop stops queueing and the streams are drained before returning: asynchronous copies into the
+   * caller's buffers must not outlive the call */
+#define SDR_TRY(expr) if ((err = (expr)) != 0) break
   while (done < n_blocks) {
     const uint32_t nb = std::min(chunk, n_blocks - done);
     const size_t w_in = (size_t)nb * SDR_BLOCK_SAMPLES * ies, w_out = (size_t)nb * SDR_BLOCK_SAMPLES * oes;
@@ -698,24 +710,25 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
     const char *srcI = (const char *)I + (size_t)done * SDR_BLOCK_SAMPLES * ies, *srcQ = (const char *)Q + (size_t)done * SDR_BLOCK_SAMPLES * ies;
     char *dst = (char *)audio + (size_t)done * SDR_BLOCK_SAMPLES * oes;
     /* H2D of chunk k into staging set b: the kernel of chunk k-2 must be done with it */
-    if (k >= 2 && dev_stream_wait(h->s_h2d, h->ev_comp[b])) return SDR_ERR_CUDA;
-    if (h2d_2d(h->d_in_i[b], cs * ies, srcI, in_pitch * ies, w_in, h->n_ch, h->s_h2d)) return SDR_ERR_CUDA;
-    if (h2d_2d(h->d_in_q[b], cs * ies, srcQ, in_pitch * ies, w_in, h->n_ch, h->s_h2d)) return SDR_ERR_CUDA;
-    if (dev_event_record(h->ev_h2d[b], h->s_h2d)) return SDR_ERR_CUDA;
+    if (k >= 2) { SDR_TRY(dev_stream_wait(h->s_h2d, h->ev_comp[b]) ? SDR_ERR_CUDA : 0); }
+    SDR_TRY(h2d_2d(h->d_in_i[b], cs * ies, srcI, in_pitch * ies, w_in, h->n_ch, h->s_h2d) ? SDR_ERR_CUDA : 0);
+    SDR_TRY(h2d_2d(h->d_in_q[b], cs * ies, srcQ, in_pitch * ies, w_in, h->n_ch, h->s_h2d) ? SDR_ERR_CUDA : 0);
+    SDR_TRY(dev_event_record(h->ev_h2d[b], h->s_h2d) ? SDR_ERR_CUDA : 0);
     /* kernel of chunk k: needs its input, and the D2H of chunk k-2 must have drained output set b */
-    if (dev_stream_wait(h->s_comp, h->ev_h2d[b])) return SDR_ERR_CUDA;
-    if (k >= 2 && dev_stream_wait(h->s_comp, h->ev_d2h[b])) return SDR_ERR_CUDA;
+    SDR_TRY(dev_stream_wait(h->s_comp, h->ev_h2d[b]) ? SDR_ERR_CUDA : 0);
+    if (k >= 2) { SDR_TRY(dev_stream_wait(h->s_comp, h->ev_d2h[b]) ? SDR_ERR_CUDA : 0); }
     int rc = sdr_batch_process_device(h, h->d_in_i[b], h->d_in_q[b], cs, in_fmt, h->d_out[b], cs, out_fmt, nb, h->s_comp);
-    if (rc) return rc;
-    if (dev_event_record(h->ev_comp[b], h->s_comp)) return SDR_ERR_CUDA;
+    SDR_TRY(rc);
+    SDR_TRY(dev_event_record(h->ev_comp[b], h->s_comp) ? SDR_ERR_CUDA : 0);
     /* D2H of chunk k */
-    if (dev_stream_wait(h->s_d2h, h->ev_comp[b])) return SDR_ERR_CUDA;
-    if (d2h_2d(dst, out_pitch * oes, h->d_out[b], cs * oes, w_out, h->n_ch, h->s_d2h)) return SDR_ERR_CUDA;
-    if (dev_event_record(h->ev_d2h[b], h->s_d2h)) return SDR_ERR_CUDA;
+    SDR_TRY(dev_stream_wait(h->s_d2h, h->ev_comp[b]) ? SDR_ERR_CUDA : 0);
+    SDR_TRY(d2h_2d(dst, out_pitch * oes, h->d_out[b], cs * oes, w_out, h->n_ch, h->s_d2h) ? SDR_ERR_CUDA : 0);
+    SDR_TRY(dev_event_record(h->ev_d2h[b], h->s_d2h) ? SDR_ERR_CUDA : 0);
     done += nb; k++;
   }
-  if (dev_sync(h->s_d2h) || dev_sync(h->s_comp) || dev_sync(h->s_h2d)) return SDR_ERR_CUDA;
-  return SDR_OK;
+#undef SDR_TRY
+  if (dev_sync(h->s_d2h) | dev_sync(h->s_comp) | dev_sync(h->s_h2d)) return err ? err : SDR_ERR_CUDA; /* all three are drained either way */
+  return err ? err : SDR_OK;
 }
 
 static int gather_words(sdr_batch_t *h, const uint32_t *ids, uint32_t n, const uint32_t *words, uint32_t nw, std::vector<float> &out) {
@@ -768,6 +781,98 @@ int sdr_batch_get_status(sdr_batch_t *h, const uint32_t *ids, uint32_t n, sdr_ch
     o.audio_filter_enabled = s.aud_on;
   }
   return SDR_OK;
+}
+
+/* ---- checkpoint: a channel's whole carry-over (setter shadow + device state) as one blob */
+namespace {
+const uint32_t STATE_MAGIC = 0x53445242u; /* "SDRB" */
+struct StateHeader { uint32_t magic, version, phase, shadow_bytes; };
+size_t state_blob_bytes() { return sizeof(StateHeader) + ((sizeof(Shadow) + 15) / 16) * 16 + sizeof(float) * SDR_STATE_WORDS; }
+/* the blanker's mask words and ring planes are indexed by (absolute block index % 3): moving a channel between handles
+ * that have processed different numbers of blocks turns the slots by the difference */
+void rotate_slots(float *w, uint32_t delta) {
+  if (delta % 3 == 0) return;
+  std::vector<float> t(w, w + SDR_STATE_WORDS);
+  for (uint32_t s = 0; s < 3; s++) {
+    const uint32_t d = (s + delta) % 3;
+    memcpy(w + W_NB_MASK + d * 32, &t[W_NB_MASK + s * 32], 32 * sizeof(float));
+    for (uint32_t pl = 0; pl < 3; pl++) memcpy(w + W_NB_RING + pl * 384 + d * 128, &t[W_NB_RING + pl * 384 + s * 128], 128 * sizeof(float));
+  }
+}
+}  // namespace
+
+size_t sdr_batch_state_bytes(void) { return state_blob_bytes(); }
+
+int sdr_batch_export_state(sdr_batch_t *h, const uint32_t *ids, uint32_t n, void *blobs) {
+  if (!h || !blobs) return fail(SDR_ERR_ARG, "export_state: bad arguments");
+  if (n == 0) return SDR_OK;
+  for (uint32_t i = 0; i < n; i++) if ((ids ? ids[i] : i) >= h->n_ch) return fail(SDR_ERR_ARG, "channel id out of range");
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  int rc = sync_config(h, h->last_stream); /* pending re-initialisations belong to the state being saved */
+  if (rc) return rc;
+  void *s = h->last_stream;
+  float *d_out = nullptr; uint32_t *d_ids = nullptr;
+  std::vector<float> words((size_t)n * SDR_STATE_WORDS);
+  do {
+    if ((rc = dev_alloc((void **)&d_out, words.size() * 4)) != 0) break;
+    if (ids) { if ((rc = dev_alloc((void **)&d_ids, (size_t)n * 4)) != 0 || (rc = h2d(d_ids, ids, (size_t)n * 4, s)) != 0) break; }
+    if (sdrk_launch_gather(h->d_state, h->ch_stride, d_ids, n, nullptr, SDR_STATE_WORDS, d_out, s)) { rc = fail(SDR_ERR_CUDA, "gather kernel launch failed"); break; }
+    h->launches++;
+    if ((rc = d2h(words.data(), d_out, words.size() * 4, s)) != 0 || (rc = dev_sync(s)) != 0) break;
+  } while (0);
+  dev_free(d_out); dev_free(d_ids);
+  if (rc) return rc;
+  const size_t bb = state_blob_bytes(), so = sizeof(StateHeader), wo = so + ((sizeof(Shadow) + 15) / 16) * 16;
+  for (uint32_t i = 0; i < n; i++) {
+    char *b = (char *)blobs + (size_t)i * bb;
+    memset(b, 0, bb);
+    StateHeader hd = {STATE_MAGIC, 1u, (uint32_t)(h->blocks_done % 3), (uint32_t)sizeof(Shadow)};
+    memcpy(b, &hd, sizeof hd);
+    memcpy(b + so, &h->sh[ids ? ids[i] : i], sizeof(Shadow));
+    memcpy(b + wo, &words[(size_t)i * SDR_STATE_WORDS], sizeof(float) * SDR_STATE_WORDS);
+  }
+  return SDR_OK;
+}
+
+int sdr_batch_import_state(sdr_batch_t *h, const uint32_t *ids, uint32_t n, const void *blobs) {
+  if (!h || !blobs) return fail(SDR_ERR_ARG, "import_state: bad arguments");
+  if (n == 0) return SDR_OK;
+  const size_t bb = state_blob_bytes(), so = sizeof(StateHeader), wo = so + ((sizeof(Shadow) + 15) / 16) * 16;
+  for (uint32_t i = 0; i < n; i++) {
+    if ((ids ? ids[i] : i) >= h->n_ch) return fail(SDR_ERR_ARG, "channel id out of range");
+    StateHeader hd; memcpy(&hd, (const char *)blobs + (size_t)i * bb, sizeof hd);
+    if (hd.magic != STATE_MAGIC || hd.version != 1u || hd.shadow_bytes != sizeof(Shadow) || hd.phase > 2)
+      return fail(SDR_ERR_ARG, "import_state: not a state blob of this library version");
+  }
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  int rc = sync_config(h, h->last_stream); /* earlier setter calls of the target channels are superseded; flush the others in order */
+  if (rc) return rc;
+  std::vector<float> words((size_t)n * SDR_STATE_WORDS);
+  std::vector<uint32_t> cid(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const char *b = (const char *)blobs + (size_t)i * bb;
+    StateHeader hd; memcpy(&hd, b, sizeof hd);
+    const uint32_t c = ids ? ids[i] : i;
+    cid[i] = c;
+    Shadow sh; memcpy(&sh, b + so, sizeof sh);
+    sh.lut_id = lut_for(h, sh.thr, sh.slope, sh.knee); /* table ids are local to a handle */
+    h->sh[c] = sh; h->pend_reset[c] = 0;
+    float *w = &words[(size_t)i * SDR_STATE_WORDS];
+    memcpy(w, b + wo, sizeof(float) * SDR_STATE_WORDS);
+    rotate_slots(w, (uint32_t)((h->blocks_done % 3) + 3 - hd.phase));
+  }
+  h->cfg_dirty = true; h->groups_dirty = true;
+  void *s = h->last_stream;
+  float *d_in = nullptr; uint32_t *d_ids = nullptr;
+  do {
+    if ((rc = dev_alloc((void **)&d_in, words.size() * 4)) != 0 || (rc = dev_alloc((void **)&d_ids, (size_t)n * 4)) != 0) break;
+    if ((rc = h2d(d_in, words.data(), words.size() * 4, s)) != 0 || (rc = h2d(d_ids, cid.data(), (size_t)n * 4, s)) != 0) break;
+    if (sdrk_launch_scatter(h->d_state, h->ch_stride, d_ids, n, d_in, s)) { rc = fail(SDR_ERR_CUDA, "scatter kernel launch failed"); break; }
+    h->launches++;
+    rc = dev_sync(s); /* the staging vectors and device buffers die here */
+  } while (0);
+  dev_free(d_in); dev_free(d_ids);
+  return rc;
 }
 
 int sdr_batch_get_role_profile(sdr_batch_t *h, uint64_t *busy28, uint64_t *total2, uint64_t *groups2) {

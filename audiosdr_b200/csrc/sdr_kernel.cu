@@ -49,14 +49,31 @@ extern "C" __global__ void sdr_fill_word_kernel(float *state, unsigned long long
   if (c < n_ch) state[(size_t)w * ch_stride + c] = v;
 }
 
-/* gather `n_words` listed state words of `n` listed channels into out[n][n_words] */
+/* Address of state word `w` of channel `c`.  Words below W_NB_RING are stored channel-fastest; the blanker ring words
+ * (plane, block slot, sample) are stored as float4 groups (sdr_pipeline.cuh, nb_group): word W_NB_RING + r is component r % 4 of
+ * group r / 4. */
+__device__ __forceinline__ size_t state_index(uint32_t w, uint32_t c, unsigned long long ch_stride) {
+  if (w < W_NB_RING) return (size_t)w * ch_stride + c;
+  const uint32_t r = w - W_NB_RING;
+  return (size_t)W_NB_RING * ch_stride + ((size_t)(r >> 2) * ch_stride + c) * 4 + (r & 3u);
+}
+
+/* gather `n_words` listed state words (all SDR_STATE_WORDS in order if `words` is null) of `n` listed channels into out[n][n_words] */
 extern "C" __global__ void sdr_gather_kernel(const float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n,
                                              const uint32_t *words, uint32_t n_words, float *out) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * n_words) return;
-  uint32_t e = i / n_words, k = i % n_words;
-  uint32_t c = chan ? chan[e] : e;
-  out[i] = state[(size_t)words[k] * ch_stride + c];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * n_words) return;
+  const uint32_t e = (uint32_t)(i / n_words), k = (uint32_t)(i % n_words);
+  const uint32_t c = chan ? chan[e] : e;
+  out[i] = state[state_index(words ? words[k] : k, c, ch_stride)];
+}
+
+/* the reverse: in[n][SDR_STATE_WORDS] -> the state words of `n` listed channels (checkpoint import) */
+extern "C" __global__ void sdr_scatter_kernel(float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n, const float *in) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * SDR_STATE_WORDS) return;
+  const uint32_t e = (uint32_t)(i / SDR_STATE_WORDS), k = (uint32_t)(i % SDR_STATE_WORDS);
+  state[state_index(k, chan[e], ch_stride)] = in[i];
 }
 
 extern "C" int sdrk_setup_device(const float *hilbert64) {
@@ -93,9 +110,16 @@ extern "C" int sdrk_launch_fill_word(float *state, unsigned long long ch_stride,
 
 extern "C" int sdrk_launch_gather(const float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n,
                                   const uint32_t *words, uint32_t n_words, float *out, void *stream) {
-  uint32_t tot = n * n_words;
+  const size_t tot = (size_t)n * n_words;
   if (tot == 0) return 0;
-  sdr_gather_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state, ch_stride, chan, n, words, n_words, out);
+  sdr_gather_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(state, ch_stride, chan, n, words, n_words, out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sdrk_launch_scatter(float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n, const float *in, void *stream) {
+  const size_t tot = (size_t)n * SDR_STATE_WORDS;
+  if (tot == 0) return 0;
+  sdr_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(state, ch_stride, chan, n, in);
   return (int)cudaGetLastError();
 }
 

@@ -22,7 +22,8 @@ int sdrk_occupancy(const SdrLaunch *L); /* resident CTAs per SM granted to this 
 int sdrk_launch_reset(float *state, unsigned long long ch_stride, const uint32_t *chan, const uint32_t *mask, uint32_t n, void *stream);
 int sdrk_launch_fill_word(float *state, unsigned long long ch_stride, uint32_t w, float v, uint32_t n_ch, void *stream);
 int sdrk_launch_gather(const float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n, const uint32_t *words,
-                       uint32_t n_words, float *out, void *stream);
+                       uint32_t n_words, float *out, void *stream); /* words == NULL: all SDR_STATE_WORDS in order */
+int sdrk_launch_scatter(float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n, const float *in, void *stream);
 #ifdef __cplusplus
 }
 #endif

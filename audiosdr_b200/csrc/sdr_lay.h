@@ -277,9 +277,11 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   L->o_c = o; o += L->nc * tile_b;
   L->smem_bytes = o;
   }
-  /* warps: one per active stage, in stage order until a measured placement is supplied (lay_place) */
+  /* warps: one per active stage, in stage order until a measured placement is supplied (lay_place).  The 32-sample plan
+   * keeps all 14 warps whatever the bucket -- stages it does not need only keep step with the others -- so that the one
+   * measured placement of stages on SM sub-partitions serves every bucket. */
   L->n_warps = 0;
-  for (int s = 0; s < SDR_STAGES; s++) if (L->active[s]) L->stage_of_warp[L->n_warps++] = (uint8_t)s;
+  for (int s = 0; s < SDR_STAGES; s++) if (L->active[s] || T == 32) L->stage_of_warp[L->n_warps++] = (uint8_t)s;
   lay_rules(L);
   return lay_check(L);
 }
@@ -288,7 +290,7 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
  * names every active stage exactly once */
 static inline int lay_place(SdrLay *L, unsigned long long map) {
   unsigned seen = 0, want = 0;
-  for (int s = 0; s < SDR_STAGES; s++) if (L->active[s]) want |= 1u << s;
+  for (int s = 0; s < SDR_STAGES; s++) if (L->active[s] || L->T == 32) want |= 1u << s;
   for (int w = 0; w < L->n_warps; w++) seen |= 1u << ((map >> (4 * w)) & 15);
   if (seen != want) return 1;
   for (int w = 0; w < L->n_warps; w++) L->stage_of_warp[w] = (uint8_t)((map >> (4 * w)) & 15);

@@ -4,9 +4,9 @@
 #define SDR_NS sdrk32
 #define SDR_LB_THREADS 448
 #define SDR_LB_BLOCKS 1
-/* 32-sample tiles: the lock-step schedule of the hand-over rules (one CTA-wide barrier per tile step) measured faster than
- * the mbarrier hand-over for every workload; -DSDR_T32_HANDOVER builds the other form for comparison */
-#ifndef SDR_T32_HANDOVER
+/* The stages run the lock-step schedule of the hand-over rules (one CTA-wide barrier per tile step): measured faster than the
+ * mbarrier hand-over on every workload and tile length; -DSDR_HANDOVER builds the other form. */
+#ifndef SDR_HANDOVER
 #define SDR_LOCKSTEP
 #endif
 #include "sdr_pipe_tu.cuh"

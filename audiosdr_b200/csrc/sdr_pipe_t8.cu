@@ -4,8 +4,9 @@
 #define SDR_NS sdrk8
 #define SDR_LB_THREADS 352
 #define SDR_LB_BLOCKS 2
-/* shorter tiles (plans that share an SM): mbarrier hand-over between the stages; -DSDR_LEAN_LOCKSTEP builds the lock-step form */
-#ifdef SDR_LEAN_LOCKSTEP
+/* The stages run the lock-step schedule of the hand-over rules (one CTA-wide barrier per tile step): measured faster than the
+ * mbarrier hand-over on every workload and tile length; -DSDR_HANDOVER builds the other form. */
+#ifndef SDR_HANDOVER
 #define SDR_LOCKSTEP
 #endif
 #include "sdr_pipe_tu.cuh"

@@ -62,20 +62,34 @@ __device__ __forceinline__ void cta_barrier() {
 }
 
 #ifdef SDR_LOCKSTEP
-/* Experiment switch (tools/build_variants.py): the lock-step schedule of the rules -- at step s the stage with delay d works
- * on tile s - d, one CTA-wide barrier per step -- to price the hand-over mechanism against the barrier. */
+/* The lock-step schedule of the hand-over rules: at step s the stage with delay d works on tile s - d, one CTA-wide barrier
+ * per step (the default: measured faster than the mbarrier hand-over below). */
 template <class Body>
 __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body) {
-  cta_barrier();
+  unsigned long long *prof = x.prof ? x.L->prof : nullptr; /* nullptr at compile time in the product kernel */
+  const long long t_loaded = prof ? clock64() : 0;
+  cta_barrier(); /* histories and tables are in shared memory */
   const uint32_t n = x.L->n_tiles;
   const int delay = x.Y->delay[stage];
   const uint32_t steps = n + (uint32_t)x.Y->dmax;
+  const bool skip = prof && ((x.L->diag_skip >> stage) & 1u);
+  long long busy = 0, waiting = 0;
+  const long long t_begin = prof ? clock64() : 0;
   x.k.reset();
 #pragma unroll 1
   for (uint32_t s = 0; s < steps; s++) {
     const long long tau = (long long)s - delay;
-    if (tau >= 0 && tau < (long long)n) { body((uint32_t)tau); x.k.advance(x); }
+    const long long t0 = prof ? clock64() : 0;
+    if (tau >= 0 && tau < (long long)n) { if (!skip) body((uint32_t)tau); x.k.advance(x); }
+    const long long t1 = prof ? clock64() : 0;
     cta_barrier();
+    if (prof) { busy += t1 - t0; waiting += clock64() - t1; }
+  }
+  if (prof && (threadIdx.x & 31) == 0) {
+    unsigned long long *row = prof + (size_t)blockIdx.x * SDR_PROF_SLOTS;
+    row[stage] += (unsigned long long)busy;
+    row[16 + stage] += (unsigned long long)waiting;
+    if (x.Y->stage_of_warp[0] == stage) { row[14] += (unsigned long long)(clock64() - t_begin); row[15] += (unsigned long long)(t_loaded - x.t0); }
   }
 }
 #else
@@ -132,6 +146,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
  * the hot loops of all stages have to share the instruction caches. */
 __device__ __forceinline__ void run_stage(const Ctx &x, int stage, int lane) {
   const bool ssb = x.Y->cls == CLS_SSB;
+  if (!x.Y->active[stage]) { pipeline_loop(x, stage, [&](uint32_t) {}); return; } /* a stage this bucket does not have: keeps step only */
   /* every 4-section cascade of the chain (IF rails, audio band-pass, AM image rails) runs through this one site */
   const bool is_if = stage == ST_IFI || stage == ST_IFQ, is_aud = stage == ST_AUD, is_img = !ssb && (stage == ST_IMGI || stage == ST_IMGQ);
   if (is_if || is_aud || is_img) {

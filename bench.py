@@ -12,7 +12,13 @@ wire format), copies inside the timed region.
   python bench.py [--gpus N --steps K --warmup W]          our CUDA path
   python bench.py --impl reference ...                      the reference's own CPU update() on all host cores
 Under torchrun every rank drives its own GPU and its own 4 096 channels (weak scaling); there is no data-path
-collective, NCCL only reduces the counters.
+collective, NCCL only reduces the counters (samples, elapsed time, parity error, status counters).
+
+The JSON line's headline keys are the config-2 workload.  The other BASELINE configurations are timed in the same run and
+reported under "workloads": config 3 (65 536 SAM channels, STRONG-scaled: the channels are sharded over the ranks),
+config 4 (16 384 channels per GPU, all seven modes, blanker + AGC + ALS) and config 5 (32 768 WSPR channels per GPU),
+each with its own ms_per_step, FP32 roofline (with that chain's flop count) and parity probe; "sustained" repeats the
+headline workload for a timed region of at least two seconds with the clock record.
 """
 import argparse
 import json
@@ -34,6 +40,19 @@ CHANNELS_PER_GPU = 4096
 CONFIG_ID = 2
 FLOP_PER_SAMPLE = 364.0     # SSB/CW core 345 + noise blanker 19 (algorithmic flop per channel-sample)
 INSTR_PER_SAMPLE = 364.0    # the same operations issued unfused (parity forbids FMA contraction)
+# SURVEY 8a cost table per workload (flop = unfused FP32 instructions per channel-sample):
+#   config 3: SAM locked 183 (288 while the envelope fallback runs);  config 5: WSPR core 345;
+#   config 4: blanker 19 + ALS 152 on top of each mode's chain: SSB/CW/WSPR 516 (5 modes of 7), AM 402, SAM 354 -> mean 476.6
+WORKLOADS = {
+    2: dict(channels=CHANNELS_PER_GPU, scaling="weak", blocks=256, flop=364.0,
+            name="BASELINE configs[1]: 4096 channels/GPU, mixed CW_LSB/CW_USB/LSB/USB, NB(10 dB)+AGC(medium)+audio BPF"),
+    3: dict(channels=65536, scaling="strong", blocks=64, flop=183.0,
+            name="BASELINE configs[2]: 65536 SAM channels (sharded over the GPUs) with carrier PLL + AGC, +-50 Hz carrier offsets"),
+    4: dict(channels=16384, scaling="weak", blocks=64, flop=(5 * 516.0 + 402.0 + 354.0) / 7.0,
+            name="BASELINE configs[3]: 16384 channels/GPU, all seven modes mixed per channel, NB + AGC + ALS auto-notch/peak, tone + impulse interference"),
+    5: dict(channels=32768, scaling="weak", blocks=64, flop=345.0,
+            name="BASELINE configs[4]: 32768 WSPR-mode channels/GPU (262144 over 8 GPUs), BareBonesWSPR setter sequence"),
+}
 BYTES_PER_SAMPLE = 12.0     # 8 B in (f32 I + f32 Q) + 4 B out per channel-sample
 HBM_FALLBACK_GBS = 6650.0
 
@@ -43,17 +62,59 @@ def shard_range(total, rank, world):
     return total * rank // world, total * (rank + 1) // world
 
 
-def gather_counters(samples, ms, world, device):
-    """Sum of samples and max of elapsed ms over ranks: the only inter-rank traffic of the whole job."""
+def reduce_counters(sums, maxs, world, device):
+    """All-reduce of two small vectors over the ranks (SUM / MAX): the only inter-rank traffic of the whole job."""
     import torch
     import torch.distributed as dist
     if world > 1 and dist.is_initialized():
-        t = torch.tensor([samples], dtype=torch.float64, device=device if device is not None else "cpu")
-        m = torch.tensor([ms], dtype=torch.float64, device=device if device is not None else "cpu")
+        t = torch.tensor(list(sums), dtype=torch.float64, device=device if device is not None else "cpu")
+        m = torch.tensor(list(maxs), dtype=torch.float64, device=device if device is not None else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        return dict(samples=float(t.item()), max_ms=float(m.item()))
-    return dict(samples=float(samples), max_ms=float(ms))
+        return [float(v) for v in t.tolist()], [float(v) for v in m.tolist()]
+    return [float(v) for v in sums], [float(v) for v in maxs]
+
+
+def gather_counters(samples, ms, world, device):
+    """Sum of samples and max of elapsed ms over ranks."""
+    s, m = reduce_counters([samples], [ms], world, device)
+    return dict(samples=s[0], max_ms=m[0])
+
+
+def gather_parity(parity, status, world, device):
+    """Parity probe and status counters of every rank folded into one record: channels and counters summed,
+    max_abs_err is the maximum, bit_exact holds only if it holds on every rank."""
+    keys = sorted(status)
+    s, m = reduce_counters([parity["channels"], parity["samples"]] + [status[k] for k in keys],
+                           [parity["max_abs_err"], 0.0 if parity["bit_exact"] else 1.0], world, device)
+    out = dict(channels=int(s[0]), samples=int(s[1]), bit_exact=m[1] == 0.0, max_abs_err=m[0], ranks=world)
+    return out, {k: int(v) for k, v in zip(keys, s[2:])}
+
+
+def pin_to_gpu_numa_node(local):
+    """Run this rank on the cores of the NUMA node its GPU hangs off (pinned host planes are then allocated there too)."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return dict(numa_node=None, note="the platform reports no NUMA node for the GPU")
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return dict(numa_node=node, cpus=len(allowed), nodes=len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]))
+    except Exception as e:
+        return dict(numa_node=None, note="not pinned: %s" % e)
 
 
 def measured_peaks():
@@ -138,26 +199,30 @@ class ClockSampler:
 
 
 def synth_planes(dev, first_channel, n_channels, n_samples, seed, config_id=CONFIG_ID):
-    """IF signals of BASELINE config 2 (headline), 3 or 5 (diagnostics), generated on the device (int16 I/Q + setter lists).
-    Two complex tones per channel (the second doubles as AM side-band energy for config 3), optional keying and impulses."""
+    """IF signals of BASELINE config 2 (headline), 3, 4 or 5, generated on the device (int16 I/Q + setter lists).
+    Up to three complex tones per channel (wanted pair or carrier + side band, interferer), optional keying and impulses."""
     import torch
     import signals as S
-    f = np.zeros((n_channels, 2)); amp = np.zeros((n_channels, 2)); keyed = np.zeros(n_channels, bool); off = np.full(n_channels, -10**9, np.int64)
+    f = np.zeros((n_channels, 3)); amp = np.zeros((n_channels, 3)); keyed = np.zeros(n_channels, bool); off = np.full(n_channels, -10**9, np.int64)
     calls = []
     for r in range(n_channels):
         c = first_channel + r
         m = S.channel_mode(config_id, c)
-        if config_id == 3:
-            df = 100.0 * S._unit(S.chash(3, c, 4)) - 50.0
-            f[r] = [6890.0 + df, 6890.0 + df + 1000.0]; amp[r] = [0.3, 0.075]
+        if config_id == 3 or (config_id == 4 and m in (S.AM, S.SAM)):
+            df = 100.0 * S._unit(S.chash(config_id, c, 4)) - 50.0
+            f[r, :2] = [6890.0 + df, 6890.0 + df + 1000.0]; amp[r, :2] = [0.3, 0.075]
         elif config_id == 5:
-            f[r] = [S._audio_to_if(S.WSPR, 1500.0), 0.0]; amp[r] = [0.05, 0.0]
+            f[r, 0] = S._audio_to_if(S.WSPR, 1500.0); amp[r, 0] = 0.05
+        elif m == S.WSPR:
+            f[r, 0] = S._audio_to_if(S.WSPR, 1500.0); amp[r, 0] = 0.2
         elif m in (S.LSB, S.USB):
             f1 = 300.0 + 900.0 * S._unit(S.chash(config_id, c, 2)); f2 = 1300.0 + 1200.0 * S._unit(S.chash(config_id, c, 3))
-            f[r] = [S._audio_to_if(m, f1), S._audio_to_if(m, f2)]; amp[r] = [0.2, 0.2]
+            f[r, :2] = [S._audio_to_if(m, f1), S._audio_to_if(m, f2)]; amp[r, :2] = [0.2, 0.2]
         else:
-            f[r] = [S._audio_to_if(m, 700.0), 0.0]; amp[r] = [0.3, 0.0]; keyed[r] = True
-        if config_id == 2:
+            f[r, 0] = S._audio_to_if(m, 700.0); amp[r, 0] = 0.3; keyed[r] = True
+        if config_id == 4:  # steady interferer at audio 1 kHz
+            f[r, 2] = S._audio_to_if(m, 1000.0); amp[r, 2] = 0.1
+        if config_id in (2, 4):
             off[r] = S.chash(config_id, c, 5) % 11025
         calls += [(r,) + tuple(e[2:]) for e in S.channel_events(config_id, c, 0)]
     sigma = 0.05 if config_id == 5 else 0.01
@@ -173,6 +238,9 @@ def synth_planes(dev, first_channel, n_channels, n_samples, seed, config_id=CONF
         key = torch.where(torch.tensor(keyed[z], device=dev)[:, None], ((t[None, :] // (44100.0 / 40.0)).long() & 1) == 0, True)
         re = az[:, 0:1] * torch.cos(ph0) * key + az[:, 1:2] * torch.cos(ph1)
         im = az[:, 0:1] * torch.sin(ph0) * key + az[:, 1:2] * torch.sin(ph1)
+        if config_id == 4:
+            ph2 = 2.0 * np.pi / 44100.0 * fz[:, 2:3] * t[None, :]
+            re = re + az[:, 2:3] * torch.cos(ph2); im = im + az[:, 2:3] * torch.sin(ph2)
         re = re + sigma * torch.randn(re.shape, generator=g, device=dev, dtype=torch.float64)
         im = im + sigma * torch.randn(im.shape, generator=g, device=dev, dtype=torch.float64)
         burst = ((t[None, :].long() - torch.tensor(off[z], device=dev)[:, None]) % 11025) < 3
@@ -208,16 +276,14 @@ def cpu_reference_rate(seconds, cores):
     return dict(value=total / busy / 1e6, unit=UNIT, cores=cores, kind="port", sample=sample)
 
 
-WORKLOAD = "BASELINE configs[1]: 4096 channels/GPU, mixed CW_LSB/CW_USB/LSB/USB, NB(10 dB)+AGC(medium)+audio BPF"
-
-
-DIAG_WORKLOADS = {3: "DIAGNOSTIC (not the headline): BASELINE configs[2], SAM channels with carrier PLL + AGC, +-50 Hz offsets",
-                  5: "DIAGNOSTIC (not the headline): BASELINE configs[4], WSPR-mode channels"}
+WORKLOAD = WORKLOADS[CONFIG_ID]["name"]
 
 
 def config_dict(nch, nblk, cfg_id=None, variant=None):
     ns = nblk * 128
-    wl = WORKLOAD if cfg_id in (None, CONFIG_ID) else "%s, %d channels/GPU" % (DIAG_WORKLOADS[cfg_id], nch)
+    wl = WORKLOADS[cfg_id or CONFIG_ID]["name"]
+    if cfg_id not in (None, CONFIG_ID):
+        wl = "NOT the headline metric: " + wl
     if variant:
         wl = "DIAGNOSTIC (not the headline): " + wl + " with switches [%s]" % variant
     return dict(workload=wl, channels_per_gpu=nch, blocks_per_step=nblk, samples_per_step=int(nch) * ns,
@@ -249,6 +315,124 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def fp32_peaks(lib):
+    """FP32 pipe microbenchmarks of the library (MEASURED_PEAKS.json has no FP32 entry): lane-instructions/s."""
+    import ctypes as C
+    ips = C.c_double(); ms = C.c_float()
+    lib.sdrk_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    res = {}
+    for kind, name in ((0, "ffma"), (1, "fmul_fadd")):
+        if lib.sdrk_fp32_peak(kind, 4096, C.byref(ips), C.byref(ms)) == 0:
+            res[name] = ips.value
+    return res
+
+
+def fp32_roofline(peaks32, flop, samples_per_launch, launch_s):
+    ach = flop * samples_per_launch / launch_s
+    return dict(bound="fp32", achieved=ach / 1e12, peak=2.0 * peaks32["ffma"] / 1e12, unit="TFLOP/s", frac=ach / (2.0 * peaks32["ffma"]),
+                peak_source="measured live: dependent-FFMA microbenchmark, 2 flop/instr",
+                issue_frac=ach / peaks32["fmul_fadd"], issue_peak_ginstr_s=peaks32["fmul_fadd"] / 1e9,
+                note="issue_frac = algorithmic unfused FP32 instructions / measured FMUL+FADD issue rate (parity forbids FMA contraction)",
+                algorithmic_flop_per_sample=flop)
+
+
+class Workload:
+    """One BASELINE configuration on this rank's GPU: planes resident in HBM, a configured handle, timing and parity."""
+
+    def __init__(self, cfg_id, rank, world, local, dev, nblk=None, variant=()):
+        import torch
+        import audiosdr_b200 as A
+        import signals as S
+        w = WORKLOADS[cfg_id]
+        self.cfg_id, self.rank, self.world, self.dev = cfg_id, rank, world, dev
+        if w["scaling"] == "strong":
+            self.first, end = shard_range(w["channels"], rank, world); self.nch = end - self.first
+        else:
+            self.nch = w["channels"]; self.first = rank * self.nch
+        self.nblk = nblk or w["blocks"]; self.ns = self.nblk * 128
+        self.I16, self.Q16, calls = synth_planes(dev, self.first, self.nch, self.ns, 0x5D120000 + cfg_id + rank, cfg_id)
+        self.If = (self.I16.to(torch.float32) / 32767.0).contiguous(); self.Qf = (self.Q16.to(torch.float32) / 32767.0).contiguous()
+        self.out = torch.empty((self.nch, self.ns), dtype=torch.float32, device=dev)
+        self.b = A.SdrBatch(self.nch, device=local)
+        self.b.configure(calls)
+        if "nonb" in variant: self.b.disableNoiseBlanker(None)
+        if "noagc" in variant: self.b.disableAGC(None)
+        if "noaud" in variant: self.b.disableAudioFilter(None)
+        if "als" in variant: self.b.enableALSfilter(None)
+        self.variant = variant
+        self.stream = torch.cuda.current_stream()
+        self.S = S
+
+    def step(self):
+        self.b.process(self.If, self.Qf, self.out, n_blocks=self.nblk, stream=self.stream)
+
+    def warm_up(self, n):
+        """n untimed steps; after the first one, sampled channels are compared with the oracle and the status getters counted."""
+        import torch
+        from oracle import oracle_lib
+        S = self.S
+        picks = sorted(set(S.sample_channels(self.cfg_id, self.nch, 12, n_shards=2)))
+        parity = status = None
+        for w in range(n):
+            self.step()
+            if w == 0 and not self.variant:
+                torch.cuda.synchronize()
+                got = self.out[picks].cpu().numpy()
+                hi, hq = self.If[picks].cpu().numpy(), self.Qf[picks].cpu().numpy()
+                ev = []
+                for row, c in enumerate(picks):
+                    ev += S.channel_events(self.cfg_id, self.first + c, row)
+                want = oracle_lib.run(hi, hq, ev, threads=os.cpu_count() or 1, want_pcm=False)["audio"]
+                fin = np.isfinite(got) & np.isfinite(want)
+                parity = dict(channels=len(picks), samples=int(want.size),
+                              bit_exact=bool(np.array_equal(got.view(np.uint32), want.view(np.uint32))),
+                              max_abs_err=float(np.max(np.abs(got[fin].astype(np.float64) - want[fin]))) if fin.any() else 0.0)
+                st = self.b.status()
+                status = dict(channels=len(st), sam_locked=sum(int(x.sam_locked) for x in st), agc_active=sum(int(x.agc_active) for x in st),
+                              nb_detected=sum(int(x.nb_detected) for x in st))
+        torch.cuda.synchronize()
+        if parity is not None:
+            parity, status = gather_parity(parity, status, self.world, self.dev)
+        return parity, status
+
+    def timed(self, steps, barrier):
+        """`steps` launches, each between its own CUDA event pair on the launching stream; max over ranks."""
+        import torch
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        l0 = self.b.launch_count
+        barrier()
+        ev0[0].record(self.stream)
+        for k in range(steps):
+            self.step()
+            ev0[k + 1].record(self.stream)
+        barrier()
+        total_ms = ev0[0].elapsed_time(ev0[-1])
+        per = [ev0[k].elapsed_time(ev0[k + 1]) for k in range(steps)]
+        cnt = gather_counters(float(self.nch) * self.ns * steps, total_ms, self.world, self.dev)
+        return dict(value=cnt["samples"] / (cnt["max_ms"] * 1e-3) / 1e6, ms_per_step=cnt["max_ms"] / steps, per_launch_ms=per,
+                    launches=int(self.b.launch_count - l0), samples=cnt["samples"])
+
+    def free(self):
+        import torch
+        del self.b, self.I16, self.Q16, self.If, self.Qf, self.out
+        torch.cuda.empty_cache()
+
+
+def side_workload(cfg_id, args, rank, world, local, dev, barrier, peaks32):
+    """One of the non-headline BASELINE configurations: device-resident rate, FP32 roofline with its own flop count, parity."""
+    w = Workload(cfg_id, rank, world, local, dev)
+    parity, status = w.warm_up(3)
+    steps = max(3, min(args.steps, 5))
+    t = w.timed(steps, barrier)
+    launch_s = float(np.mean(t["per_launch_ms"])) * 1e-3
+    rec = dict(workload=WORKLOADS[cfg_id]["name"], metric=METRIC, unit=UNIT, value=t["value"], n_gpus=world, scaling=WORKLOADS[cfg_id]["scaling"],
+               channels_this_rank=w.nch, blocks_per_step=w.nblk, steps=steps, warmup=3, ms_per_step=t["ms_per_step"], gpu_launches=t["launches"],
+               roofline_fp32=fp32_roofline(peaks32, WORKLOADS[cfg_id]["flop"], float(w.nch) * w.ns, launch_s) if peaks32 else None,
+               hbm_gbs=BYTES_PER_SAMPLE * float(w.nch) * w.ns / launch_s / 1e9, parity=parity, status=status)
+    w.free()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,8 +443,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", type=int, default=CONFIG_ID, choices=[2, 3, 5],
-                    help="diagnostics only: BASELINE config 3 (SAM, 65536 ch) or 5 (WSPR, 32768 ch/GPU) instead of the headline config 2")
+    ap.add_argument("--workload", type=int, default=CONFIG_ID, choices=[2, 3, 4, 5],
+                    help="diagnostics only: make BASELINE config 3 / 4 / 5 the line's workload instead of the headline config 2")
+    ap.add_argument("--only-headline", action="store_true", help="skip the config 3 / 4 / 5 workloads and the sustained run")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--variant", default="", help="diagnostics only: comma list of nonb,noagc,noaud,als (changes the workload!)")
     ap.add_argument("--role-profile", action="store_true", help="per-stage busy fractions (adds clock reads; not for headline numbers)")
     args = ap.parse_args()
@@ -275,6 +461,7 @@ def main():
     from audiosdr_b200 import api
     A.build_library()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU path"
+    affinity = pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -282,42 +469,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = api.load_library()
     cfg_id = args.workload
-    nch = {2: CHANNELS_PER_GPU, 3: 65536, 5: 32768}[cfg_id]
-    nblk = args.blocks_per_step if cfg_id == 2 else min(args.blocks_per_step, 64)
-    ns = nblk * 128
-    first = rank * nch
-    I16, Q16, calls = synth_planes(dev, first, nch, ns, 0x5D120000 + cfg_id + rank, cfg_id)
-    If = (I16.to(torch.float32) / 32767.0).contiguous(); Qf = (Q16.to(torch.float32) / 32767.0).contiguous()
-    out = torch.empty((nch, ns), dtype=torch.float32, device=dev)
+    diagnostic = cfg_id != CONFIG_ID or bool(args.variant) or args.role_profile
     if args.role_profile:
         os.environ["SDR_ROLE_PROFILE"] = "1"
-    b = A.SdrBatch(nch, device=local)
-    b.configure(calls)
-    variant = [v for v in args.variant.split(",") if v]
-    if "nonb" in variant: b.disableNoiseBlanker(None)
-    if "noagc" in variant: b.disableAGC(None)
-    if "noaud" in variant: b.disableAudioFilter(None)
-    if "als" in variant: b.enableALSfilter(None)
-    stream = torch.cuda.current_stream()
-
-    # ---- warm-up, with an untimed parity probe of sampled channels against the oracle on step 0
-    import signals as S
-    from oracle import oracle_lib
-    picks = sorted(set(S.sample_channels(cfg_id, nch, 12, n_shards=2)))
-    parity = None
-    for w in range(max(args.warmup, 3)):
-        b.process(If, Qf, out, n_blocks=nblk, stream=stream)
-        if w == 0 and not variant:
-            torch.cuda.synchronize()
-            got = out[picks].cpu().numpy()
-            hi, hq = If[picks].cpu().numpy(), Qf[picks].cpu().numpy()
-            ev = []
-            for row, c in enumerate(picks):
-                ev += S.channel_events(cfg_id, first + c, row)
-            want = oracle_lib.run(hi, hq, ev, threads=os.cpu_count() or 1, want_pcm=False)["audio"]
-            parity = dict(channels=len(picks), samples=int(want.size), bit_exact=bool(np.array_equal(got.view(np.uint32), want.view(np.uint32))),
-                          max_abs_err=float(np.max(np.abs(got.astype(np.float64) - want))))
-    torch.cuda.synchronize()
+    variant = tuple(v for v in args.variant.split(",") if v)
+    W = Workload(cfg_id, rank, world, local, dev, nblk=args.blocks_per_step if cfg_id == CONFIG_ID else None, variant=variant)
+    nch, nblk, ns, b, I16, Q16 = W.nch, W.nblk, W.ns, W.b, W.I16, W.Q16
+    parity, status = W.warm_up(max(args.warmup, 3))
 
     def barrier():
         if world > 1:
@@ -326,21 +484,19 @@ def main():
 
     # ---- device-resident timing: K launches, each timed with its own CUDA event pair on the launching stream
     clk = ClockSampler(local); clk.start()
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    l0 = b.launch_count
-    barrier()
-    ev0[0].record(stream)
-    for k in range(args.steps):
-        b.process(If, Qf, out, n_blocks=nblk, stream=stream)
-        ev0[k + 1].record(stream)
-    barrier()
-    launches = b.launch_count - l0
+    T = W.timed(args.steps, barrier)
     clocks = clk.stop()
+    launches, per_launch_ms, value = T["launches"], T["per_launch_ms"], T["value"]
     role_profile = b.role_profile() if args.role_profile else None  # before the chunked e2e launches dilute the per-launch average
-    total_ms = ev0[0].elapsed_time(ev0[-1])
-    per_launch_ms = [ev0[k].elapsed_time(ev0[k + 1]) for k in range(args.steps)]
-    cnt = gather_counters(float(nch) * ns * args.steps, total_ms, world, dev)
-    value = cnt["samples"] / (cnt["max_ms"] * 1e-3) / 1e6
+
+    # ---- the same workload for a timed region of seconds: sustained clocks (config 5 streams for 120 s per channel)
+    sustained = None
+    if not diagnostic and not args.only_headline and args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(np.ceil(args.sustained_seconds * 1e3 / max(T["ms_per_step"], 1e-3))))
+        clk2 = ClockSampler(local); clk2.start()
+        Ts = W.timed(n_sus, barrier)
+        sustained = dict(value=Ts["value"], unit=UNIT, steps=n_sus, ms_per_step=Ts["ms_per_step"], seconds=Ts["ms_per_step"] * n_sus * 1e-3,
+                         clocks=clk2.stop())
 
     # ---- end to end through the C ABI with HOST buffers (pinned int16 in, int16 out), copies inside the timed region
     hI = torch.empty((nch, ns), dtype=torch.int16).pin_memory(); hQ = torch.empty_like(hI).pin_memory()
@@ -400,24 +556,25 @@ def main():
                     traffic=traffic, peak_source=peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
                     kernel="sdr_pipeline_kernel", algorithmic_bytes_per_sample=BYTES_PER_SAMPLE,
                     note="BASELINE.json quotes % of HBM roofline; the binding roofline of this chain is the FP32 pipe, see roofline_fp32")
-    fp32 = None
+    flop = WORKLOADS[cfg_id]["flop"] + (152.0 if "als" in variant else 0.0) - (19.0 if "nonb" in variant and cfg_id == 2 else 0.0)
+    peaks32 = None
     try:
-        import ctypes as C
-        ips = C.c_double(); ms = C.c_float()
-        lib.sdrk_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
-        res = {}
-        for kind, name in ((0, "ffma"), (1, "fmul_fadd")):
-            if lib.sdrk_fp32_peak(kind, 4096, C.byref(ips), C.byref(ms)) == 0:
-                res[name] = ips.value
-        ach_flops = FLOP_PER_SAMPLE * samples_per_launch / launch_s
-        fp32 = dict(bound="fp32", achieved=ach_flops / 1e12, peak=2.0 * res["ffma"] / 1e12, unit="TFLOP/s",
-                    frac=ach_flops / (2.0 * res["ffma"]), peak_source="measured live: dependent-FFMA microbenchmark, 2 flop/instr",
-                    issue_frac=INSTR_PER_SAMPLE * samples_per_launch / launch_s / res["fmul_fadd"],
-                    issue_peak_ginstr_s=res["fmul_fadd"] / 1e9,
-                    note="issue_frac = algorithmic unfused FP32 instructions / measured FMUL+FADD issue rate (parity forbids FMA contraction)",
-                    algorithmic_flop_per_sample=FLOP_PER_SAMPLE)
+        peaks32 = fp32_peaks(lib)
+        fp32 = fp32_roofline(peaks32, flop, samples_per_launch, launch_s)
     except Exception as e:  # the microbenchmark is evidence, not the product
-        fp32 = dict(error=str(e))
+        fp32 = dict(error=str(e)); peaks32 = None
+
+    # ---- free the headline planes, then the other BASELINE configurations (each sized for one GPU)
+    del hI, hQ, hO, nI, nQ, nO
+    W.free()
+    workloads = None
+    if not diagnostic and not args.only_headline:
+        workloads = {}
+        for other in (3, 4, 5):
+            try:
+                workloads["config%d" % other] = side_workload(other, args, rank, world, local, dev, barrier, peaks32)
+            except Exception as e:  # a side workload must not take the headline line down with it
+                workloads["config%d" % other] = dict(error="%s: %s" % (type(e).__name__, e))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -425,13 +582,14 @@ def main():
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                    ms_per_step=cnt["max_ms"] / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    ms_per_step=T["ms_per_step"], higher_is_better=True, scaling=WORKLOADS[cfg_id]["scaling"], vs_baseline=None, dtype="f32",
                     data="synthetic",
                     config=config_dict(nch, nblk, cfg_id, args.variant or None),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_fp32=fp32, cpu_baseline=cpu,
                     role_profile=role_profile, variant=args.variant or None,
                     diagnostic_workload=(None if cfg_id == CONFIG_ID else "BASELINE configs[%d], %d channels/GPU: NOT the headline metric" % (cfg_id - 1, nch)),
-                    parity=parity, per_launch_ms=dict(mean=float(np.mean(per_launch_ms)), min=float(np.min(per_launch_ms)), max=float(np.max(per_launch_ms))))
+                    parity=parity, status=status, host_affinity=affinity, sustained=sustained, workloads=workloads,
+                    per_launch_ms=dict(mean=float(np.mean(per_launch_ms)), min=float(np.min(per_launch_ms)), max=float(np.max(per_launch_ms))))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -31,11 +31,12 @@ struct Channels {
   const uint32_t *ids;
   uint32_t n;
   uint32_t one;
-  Channels() : ids(nullptr), n(0), one(0) {}                                   /* all channels */
-  Channels(uint32_t c) : ids(&one), n(1), one(c) {}                            /* NOLINT: implicit on purpose */
-  Channels(int c) : ids(&one), n(1), one((uint32_t)c) {}                       /* NOLINT */
-  Channels(const std::vector<uint32_t> &v) : ids(v.data()), n((uint32_t)v.size()), one(0) {} /* NOLINT */
-  Channels(const Channels &o) : ids(o.ids == &o.one ? &one : o.ids), n(o.n), one(o.one) {}
+  bool every; /* all channels of the handle (an EMPTY list selects nothing: `every` is what tells the two apart) */
+  Channels() : ids(nullptr), n(0), one(0), every(true) {}                                    /* all channels */
+  Channels(uint32_t c) : ids(&one), n(1), one(c), every(false) {}                            /* NOLINT: implicit on purpose */
+  Channels(int c) : ids(&one), n(1), one((uint32_t)c), every(false) {}                       /* NOLINT */
+  Channels(const std::vector<uint32_t> &v) : ids(v.data()), n((uint32_t)v.size()), one(0), every(false) {} /* NOLINT */
+  Channels(const Channels &o) : ids(o.ids == &o.one ? &one : o.ids), n(o.n), one(o.one), every(o.every) {}
 };
 static const Channels all;
 
@@ -134,7 +135,8 @@ class SdrBatch {
 
  private:
   void set(const Channels &c, uint32_t setter, float a0 = 0.f, float a1 = 0.f, float a2 = 0.f) {
-    check(sdr_batch_set(h_, c.ids, c.n, setter, a0, a1, a2), "sdr_batch_set");
+    if (!c.every && c.n == 0) return; /* an empty selection: nothing to do (the C call reads ids == NULL as "all channels") */
+    check(sdr_batch_set(h_, c.every ? nullptr : c.ids, c.n, setter, a0, a1, a2), "sdr_batch_set");
   }
   static void check(int rc, const char *what) {
     if (rc != SDR_OK) throw std::runtime_error(std::string(what) + ": " + sdr_batch_last_error());

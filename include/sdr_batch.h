@@ -11,7 +11,7 @@
  *   sdr_batch_create        AudioSDR::AudioSDR() -> init()                      H:77-79, C:174-185
  *   sdr_batch_set           any one public setter of the class                  H:88-152 (bodies C:187-311,356-398,498-566,653-682)
  *   sdr_batch_configure     a whole setter sequence per channel, e.g. the sketch's  INO:87-102,129
- *   sdr_batch_process_*     AudioStream::update_all() -> AudioSDR::update()     C:39-168
+ *   sdr_batch_process[_*]   AudioStream::update_all() -> AudioSDR::update()     C:39-168
  *                            (receiveWritable(0/1) C:46-47 = the I/Q planes in; transmit(blockI,0/1) C:164-165 = the audio plane out)
  *   sdr_batch_get_status    the getters                                          C:224-230,255-273,295,371-381,495,507-512,568-600,660-665,752-757
  *   sdr_batch_destroy       (object lifetime)
@@ -151,6 +151,8 @@ int sdr_batch_configure(sdr_batch_t *h, const sdr_setter_call *calls, uint32_t n
  * in_fmt/out_fmt: SDR_FMT_*; pitches in elements.  Advances every channel by n_blocks blocks. */
 int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt,
                              void *audio, size_t out_pitch, int out_fmt, uint32_t n_blocks, void *cuda_stream);
+/* The same call in its plainest form: float32 planes, rows densely packed (pitch = 128 * n_blocks elements). */
+int sdr_batch_process(sdr_batch_t *h, const float *I, const float *Q, float *audio, uint32_t n_blocks, void *cuda_stream);
 /* Same through HOST buffers (pinned or pageable): H2D copy, kernel, D2H copy, synchronous on return. */
 int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt,
                            void *audio, size_t out_pitch, int out_fmt, uint32_t n_blocks);
@@ -161,6 +163,16 @@ int sdr_batch_get_status(sdr_batch_t *h, const uint32_t *channel_ids, uint32_t n
 int sdr_batch_get_agc_lookup(sdr_batch_t *h, uint32_t channel, float *out129);
 /* Debug/test tap: raw per-channel state word (see audiosdr_b200/csrc/sdr_types.h). */
 int sdr_batch_peek_state(sdr_batch_t *h, uint32_t channel, uint32_t word, float *out);
+
+/* Checkpoint / migration.  A channel's whole carry-over -- the configuration its setters have built up (the members the
+ * reference's setters write, H:164-330) and everything update() carries from block to block (filter delay lines H:191-195,
+ * Hilbert rings and NCO phases C:41-44, AGC H:208-232, PLL C:690-694 / H:263-274, ALS taps and history H:198-205, blanker
+ * rings, mask and average H:235-246) -- as one opaque blob of sdr_batch_state_bytes() bytes per channel.  Importing a blob
+ * into any channel of any handle of the same library version (another GPU, another process, a handle that has run a
+ * different number of blocks) continues the stream bit for bit.  Both calls synchronise the handle's last stream. */
+size_t sdr_batch_state_bytes(void);
+int sdr_batch_export_state(sdr_batch_t *h, const uint32_t *channel_ids, uint32_t n, void *blobs);
+int sdr_batch_import_state(sdr_batch_t *h, const uint32_t *channel_ids, uint32_t n, const void *blobs);
 
 /* Diagnostics: per-stage busy cycles of the pipeline kernel, summed over groups and launches since create.
  * Only recorded when the environment variable SDR_ROLE_PROFILE=1 was set at create (costs two clock reads per

@@ -200,10 +200,24 @@ int sdrk_launch_fill_word(float *state, unsigned long long ch_stride, uint32_t w
   return 0;
 }
 
+static size_t emu_state_index(uint32_t w, uint32_t c, unsigned long long ch_stride) {
+  if (w < W_NB_RING) return (size_t)w * ch_stride + c;
+  const uint32_t r = w - W_NB_RING;
+  return (size_t)W_NB_RING * ch_stride + ((size_t)(r >> 2) * ch_stride + c) * 4 + (r & 3u);
+}
+
 int sdrk_launch_gather(const float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n, const uint32_t *words,
                        uint32_t n_words, float *out, void *) {
   for (uint32_t e = 0; e < n; e++)
-    for (uint32_t k = 0; k < n_words; k++) out[(size_t)e * n_words + k] = state[(size_t)words[k] * ch_stride + (chan ? chan[e] : e)];
+    for (uint32_t k = 0; k < n_words; k++) out[(size_t)e * n_words + k] = state[emu_state_index(words ? words[k] : k, chan ? chan[e] : e, ch_stride)];
   return 0;
 }
+
+int sdrk_launch_scatter(float *state, unsigned long long ch_stride, const uint32_t *chan, uint32_t n, const float *in, void *) {
+  for (uint32_t e = 0; e < n; e++)
+    for (uint32_t k = 0; k < SDR_STATE_WORDS; k++) state[emu_state_index(k, chan[e], ch_stride)] = in[(size_t)e * SDR_STATE_WORDS + k];
+  return 0;
+}
+
+int sdrk_occupancy(const SdrLaunch *) { return 0; }
 }

@@ -209,3 +209,58 @@ def test_emulated_sam_driven_out_of_lock_and_back(oracle, emu_lib, monkeypatch):
     a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(37, 1, 90), return_batch=True)
     assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
     assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+
+
+def migration_case(lib, I, Q, ev, device=None):
+    """Runs channels for a while on handle A, moves them -- blobs of export_state -- into OTHER channel slots of handle B
+    that has already processed a different number of blocks (the blanker's block-indexed ring slots turn), and continues
+    there.  Returns the concatenated audio of the moved channels."""
+    import audiosdr_b200 as A
+    nch, ns = I.shape
+    nblk = ns // 128
+    cut = nblk // 2 + 1
+    a = A.SdrBatch(nch, _lib=lib)
+    a.configure([(None if e[0] == 0xFFFFFFFF else e[0], e[2]) + tuple(e[3:]) for e in ev if e[1] == 0])
+    first = np.empty((nch, cut * 128), np.float32)
+    if device is None:
+        a.process_host(I[:, :cut * 128], Q[:, :cut * 128], first)
+    else:
+        import torch
+        dI, dQ = torch.from_numpy(I).to(device), torch.from_numpy(Q).to(device)
+        dO = torch.empty((nch, ns), dtype=torch.float32, device=device)
+        a.process(dI[:, :cut * 128], dQ[:, :cut * 128], dO[:, :cut * 128], n_blocks=cut); torch.cuda.synchronize()
+        first = dO[:, :cut * 128].cpu().numpy()
+    blobs = a.export_state()
+    b = A.SdrBatch(nch + 5, _lib=lib)
+    z = np.zeros((nch + 5, 2 * 128), np.int16)
+    b.process_host(z, z, np.empty((nch + 5, 2 * 128), np.float32))      # B is two blocks old: other ring-slot phase than A (cut blocks)
+    perm = np.random.default_rng(5).permutation(nch + 5)[:nch]           # other slots, other lanes, other groups
+    assert len(set(perm.tolist())) == nch
+    b.import_state(perm, blobs)
+    I2 = np.zeros((nch + 5, ns - cut * 128), np.int16); Q2 = np.zeros_like(I2)
+    I2[perm] = I[:, cut * 128:]; Q2[perm] = Q[:, cut * 128:]
+    second = np.empty((nch + 5, ns - cut * 128), np.float32)
+    b.process_host(I2, Q2, second)
+    return np.concatenate([first, second[perm]], 1)
+
+
+def test_emulated_state_export_import_continues_bit_exact(oracle, emu_lib):
+    I, Q, ev = S.make(4, list(range(44)), 15)
+    want = oracle.run(I, Q, ev, threads=4)["audio"]
+    got = migration_case(emu_lib, I, Q, ev)
+    assert harness.bits_equal(got, want), harness.describe_mismatch(got, want)
+
+
+@pytest.mark.parametrize("sched", ["lockstep", "consumers", "random:3/late"])
+@pytest.mark.parametrize("tile,ctas", [(16, 2), (8, 2), (16, 1)])
+@pytest.mark.parametrize("cfg,nch,nblk", [(1, 1, 24), (3, 6, 30), (5, 5, 30)])
+def test_emulated_short_tile_plans(oracle, emu_lib, monkeypatch, cfg, nch, nblk, tile, ctas, sched):
+    """Buckets without blanker and ALS can run 16- or 8-sample tiles in a fraction of the shared memory (several groups
+    per SM; the product picks 16-sample tiles for large ENV buckets): same bits for every tile length and ring budget."""
+    set_schedule(monkeypatch, sched)
+    monkeypatch.setenv("SDR_TILE_SSB", str(tile)); monkeypatch.setenv("SDR_TILE_ENV", str(tile)); monkeypatch.setenv("SDR_CTAS_PER_SM", str(ctas))
+    I, Q, ev = S.make(cfg, list(range(nch)), nblk)
+    o = oracle.run(I, Q, ev, threads=4)
+    a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(7, 1, 13), return_batch=True)
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)

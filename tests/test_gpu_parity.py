@@ -104,6 +104,15 @@ def test_cuda_lone_mode_switch(cuda_lib, oracle, dev):
     assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
 
 
+def test_cuda_state_export_import_continues_bit_exact(cuda_lib, oracle, dev):
+    """Checkpoint / migration: channels moved between handles (other slot, other ring phase) continue bit for bit."""
+    from test_emu_pipeline import migration_case
+    I, Q, ev = S.make(4, list(range(70)), 21)
+    want = oracle.run(I, Q, ev, threads=4)["audio"]
+    got = migration_case(cuda_lib, I, Q, ev, device=dev)
+    assert_same(got, want)
+
+
 def test_cuda_setter_fuzz(cuda_lib, oracle, dev):
     rng = np.random.default_rng(4321)
     I, Q, ev = S.make(4, list(range(64)), 48)
