@@ -597,6 +597,7 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
   /* configuration uploads, state resets and the kernels of this call must not overtake work an earlier call queued on
    * another stream (they share the handle's state and tables) */
   if (h->launches && stream != h->last_stream && dev_sync(h->last_stream)) return SDR_ERR_CUDA;
+  if (getenv("SDR_MAP_SEARCH")) h->groups_dirty = true; /* tools/map_search.py: plan (and read the placement variables) at every call */
   if ((rc = sync_config(h, stream)) != 0) return rc;
   SdrLaunch L;
   memset(&L, 0, sizeof L);

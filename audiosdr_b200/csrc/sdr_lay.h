@@ -37,10 +37,15 @@ enum { LF_NB = 1u, LF_ALS = 2u };
 /* The plan of every 32-sample-tile launch is the same (whatever optional stages the bucket has): offsets and ring depths
  * are compile-time constants of the 32-sample kernel, and a group with all stages fills the SM's shared memory. */
 enum {
-  LAY32_NR = 5, LAY32_NI = 6, LAY32_HQ_TILES = 12, LAY32_NA_SSB = 3, LAY32_NA_ENV = 5, LAY32_NC = 6, LAY32_NZ = 5, LAY32_NZ2 = 3,
+#ifdef SDR_HANDOVER /* (experiment build: the hand-over barriers need room, taken from the Hilbert Q ring) */
+  LAY32_HQ_TILES = 12, LAY32_BAR_BYTES = SDR_STAGES * SDR_BAR_W * 8,
+#else
+  LAY32_HQ_TILES = 16, LAY32_BAR_BYTES = 0, /* 16 tiles = 512 samples: ring positions wrap with a mask */
+#endif
+  LAY32_NR = 5, LAY32_NI = 6, LAY32_NA_SSB = 3, LAY32_NA_ENV = 5, LAY32_NC = 6, LAY32_NZ = 5, LAY32_NZ2 = 3,
   LAY32_TILE = 32 * SDR_LANES * 4,
   LAY32_SINE = 0, LAY32_LUT = 1152, LAY32_NCOT = 3328, LAY32_CID = 3584, LAY32_BAR = 3712,
-  LAY32_NBS = LAY32_BAR + SDR_STAGES * SDR_BAR_W * 8,
+  LAY32_NBS = LAY32_BAR + LAY32_BAR_BYTES,
   LAY32_INS = LAY32_NBS + 32 * SDR_LANES * 16,
   LAY32_OUTS = LAY32_INS + 2 * SDR_LANES * 36 * 4,
   LAY32_R = LAY32_OUTS + SDR_LANES * 36 * 4,
@@ -238,7 +243,7 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   L->o_lut = o; o += lay_align(SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE * 4, 128);
   L->o_ncot = o; o += 256;
   L->o_cid = o; o += 128;
-  L->o_bar = o; o += SDR_STAGES * SDR_BAR_W * 8;
+  L->o_bar = o; o += LAY32_BAR_BYTES; /* hand-over barriers: only the -DSDR_HANDOVER build has them */
   if (cls == CLS_ENV) { L->o_flags = o; o += 8 * SDR_LANES * 4; L->o_carr = o; o += 8 * SDR_LANES * 4; }
   if (nb) { L->o_nbs = o; o += 32 * SDR_LANES * 16; L->o_mask = o; o += 3 * 128 * SDR_LANES; }
   if (als) { L->o_alsc = o; o += 128 * SDR_LANES * 4; }

@@ -75,12 +75,12 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
   const bool skip = prof && ((x.L->diag_skip >> stage) & 1u);
   long long busy = 0, waiting = 0;
   const long long t_begin = prof ? clock64() : 0;
-  x.k.reset();
+  x.slots_reset();
 #pragma unroll 1
   for (uint32_t s = 0; s < steps; s++) {
     const long long tau = (long long)s - delay;
     const long long t0 = prof ? clock64() : 0;
-    if (tau >= 0 && tau < (long long)n) { if (!skip) body((uint32_t)tau); x.k.advance(x); }
+    if (tau >= 0 && tau < (long long)n) { if (!skip) body((uint32_t)tau); x.slots_advance(); }
     const long long t1 = prof ? clock64() : 0;
     cta_barrier();
     if (prof) { busy += t1 - t0; waiting += clock64() - t1; }
@@ -104,7 +104,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
   const uint32_t my_bar = bars + (uint32_t)x.Y->bar_of[stage] * (SDR_BAR_W * 8u);
   long long busy = 0, waiting = 0;
   const long long t_begin = prof ? clock64() : 0;
-  x.k.reset();
+  x.slots_reset();
 #pragma unroll 1
   for (uint32_t t = 0; t < n; t++) {
     const long long tw = prof ? clock64() : 0;
@@ -128,7 +128,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
     if (!skip) body(t);
     __syncwarp();
     if ((threadIdx.x & 31) == 0) bar_arrive(my_bar + (t & (SDR_BAR_W - 1)) * 8u);
-    x.k.advance(x);
+    x.slots_advance();
     if (prof) { const long long t1 = clock64(); waiting += t0 - tw; busy += t1 - t0; }
   }
   if (prof && (threadIdx.x & 31) == 0) {
@@ -214,11 +214,13 @@ __device__ __forceinline__ void pipeline_cta(const SdrLaunch &L, unsigned char *
   const int nthr = (int)blockDim.x;
   for (int i = threadIdx.x; i < 257; i += nthr) x.f(x.o_sine())[i] = L.tabs->sine[i];
   if (threadIdx.x < SDR_LANES) reinterpret_cast<int *>(smem + x.o_cid())[threadIdx.x] = x.G->cid[threadIdx.x];
+#ifndef SDR_LOCKSTEP
   {
     const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem + x.o_bar());
     for (int i = threadIdx.x; i < SDR_STAGES * SDR_BAR_W; i += nthr) bar_init(bars + 8u * (uint32_t)i, (uint32_t)x.Y->bar_count[i / SDR_BAR_W]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+#endif
   __syncthreads(); /* stage IN requests its first tile from load(), which needs the channel ids */
   for (int i = threadIdx.x; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i += nthr) { /* the group's AGC tables */
     const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];

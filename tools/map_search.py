@@ -19,14 +19,16 @@ ap.add_argument("--blocks", type=int, default=128)
 ap.add_argument("--start", default="")
 args = ap.parse_args()
 cfg_id = 2 if args.cls == "ssb" else 3
-nch = 4096
+nch = 4096 if args.cls != "envlean" else 16384   # envlean: enough groups for the two-per-SM plan (sdr_host.cpp, plan_bucket)
+os.environ["SDR_MAP_SEARCH"] = "1"               # the host re-plans at every call, so that it reads the placement variable again
 dev = torch.device("cuda:0")
 I16, Q16, calls = bench.synth_planes(dev, 0, nch, args.blocks * 128, 1234, cfg_id)
 If, Qf = I16.float() / 32767.0, Q16.float() / 32767.0
 out = torch.empty((nch, args.blocks * 128), dtype=torch.float32, device=dev)
 b = api.SdrBatch(nch)
 b.configure(calls)
-var = "SDR_MAP_SSB" if args.cls == "ssb" else "SDR_MAP_ENV"
+var = {"ssb": "SDR_MAP_SSB", "env": "SDR_MAP_ENV", "envlean": "SDR_MAP_ENV_LEAN"}[args.cls]
+NW = 11 if args.cls == "envlean" else 14
 stream = torch.cuda.current_stream()
 
 def pack(perm):
@@ -45,7 +47,7 @@ def measure(perm, reps=3):
 def canon(perm):  # the four Hilbert warps (SSB stages 5..8) are interchangeable
     return tuple(5 if (args.cls == "ssb" and 5 <= s <= 8) else s for s in perm)
 
-start = [int(c, 16) for c in reversed(args.start)] if args.start else [5, 6, 7, 8, 2, 3, 11, 4, 9, 12, 10, 1, 0, 13]
+start = [int(c, 16) for c in reversed(args.start)] if args.start else ([0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11] if args.cls == "envlean" else [5, 6, 7, 8, 2, 3, 11, 4, 9, 12, 10, 1, 0, 13])
 for _ in range(3):
     measure(start)
 seen = {}
@@ -56,7 +58,7 @@ t_end = time.time() + args.seconds
 cur, cur_t = list(best_perm), best_t
 stale = 0
 while time.time() < t_end:
-    i, j = random.sample(range(14), 2)
+    i, j = random.sample(range(NW), 2)
     cand = list(cur); cand[i], cand[j] = cand[j], cand[i]
     key = canon(cand)
     if key in seen or canon(cand) == canon(cur):
@@ -76,7 +78,7 @@ while time.time() < t_end:
     if stale > 120:   # restart from a random shuffle of the best
         cur = list(best_perm)
         for _ in range(4):
-            i, j = random.sample(range(14), 2); cur[i], cur[j] = cur[j], cur[i]
+            i, j = random.sample(range(NW), 2); cur[i], cur[j] = cur[j], cur[i]
         cur_t, stale = measure(cur, 5), 0
 print("evals/s %.1f" % (len(seen) / args.seconds))
 print("evaluated %d placements; best %s %.3f ms (%.0f Msps)" % (len(seen), pack(best_perm), best_t, nch * args.blocks * 128 / best_t / 1e3))
