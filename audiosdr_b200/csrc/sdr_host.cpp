@@ -308,24 +308,34 @@ int env_int(const char *name, int dflt) { const char *e = getenv(name); return e
 int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
   /* Measured: the SSB class is bound by its four Hilbert warps per SM whatever the tile length, so it
    * stays on the 32-sample plan; an ENV group is bound by the latency of its one PLL warp, so ENV buckets without blanker
-   * and ALS run 16-sample tiles in half the shared memory, two groups per SM -- when there are enough groups to share. */
+   * and ALS run shorter tiles in a fraction of the shared memory -- 16-sample tiles, two groups per SM; SAM-only buckets
+   * 8-sample tiles with the light stages merged (7 warps), three groups per SM -- when there are enough groups to share. */
   int T = 32, ctas = 1;
-  if (cls == CLS_ENV && !(feat & (LF_NB | LF_ALS)) && b.count > (uint32_t)n_sm) { T = 16; ctas = 2; }
+  const bool lean = !(feat & (LF_NB | LF_ALS));
+  if (cls == CLS_ENV && lean && b.count > (uint32_t)n_sm) {
+    if ((feat & LF_SAM) && b.count > 2u * (uint32_t)n_sm) { T = 8; ctas = 3; }
+    else { T = 16; ctas = 2; }
+  }
   const int t_env = env_int(cls == CLS_SSB ? "SDR_TILE_SSB" : "SDR_TILE_ENV", 0);
-  if (t_env && !(feat & (LF_NB | LF_ALS))) { T = t_env; ctas = T == 32 ? 1 : 2; }
+  if (t_env && lean) { T = t_env; ctas = T == 32 ? 1 : 2; }
   const int c_env = env_int("SDR_CTAS_PER_SM", 0);
   if (c_env > 0) ctas = c_env;
+  if (env_int("SDR_NO_MERGE", 0)) feat &= ~(uint32_t)LF_SAM;
   const int slack = env_int("SDR_SLACK", 0); /* extra ring slots only matter to the hand-over build (-DSDR_HANDOVER) */
   const int budget = (233472 - 1024 * ctas) / ctas; /* an SM has 228 KB, each resident CTA costs 1 KB of it */
   int rc = lay_build(&b.lay, cls, feat, T, budget > 232448 ? 232448 : budget, slack);
   if (rc) rc = lay_build(&b.lay, cls, feat, 32, 232448, 0);
   if (rc) return rc;
-  /* measured placements exist for the 14-warp launches */
+  /* measured placements */
   if (b.lay.n_warps == SDR_STAGES) {
     unsigned long long m = cls == CLS_SSB ? SDR_MAP_SSB_DEFAULT : SDR_MAP_ENV_DEFAULT;
     if (const char *e = getenv(cls == CLS_SSB ? "SDR_MAP_SSB" : "SDR_MAP_ENV")) m = strtoull(e, nullptr, 16);
     lay_place(&b.lay, m);
-  } else if (const char *e = getenv(cls == CLS_SSB ? "SDR_MAP_SSB_LEAN" : "SDR_MAP_ENV_LEAN")) lay_place(&b.lay, strtoull(e, nullptr, 16));
+  } else if (cls == CLS_ENV && b.lay.n_warps == 11) {
+    unsigned long long m = SDR_MAP_ENV_LEAN_DEFAULT;
+    if (const char *e = getenv("SDR_MAP_ENV_LEAN")) m = strtoull(e, nullptr, 16);
+    lay_place(&b.lay, m);
+  } else if (const char *e = getenv("SDR_MAP_SSB_LEAN")) lay_place(&b.lay, strtoull(e, nullptr, 16));
   return 0;
 }
 
@@ -335,15 +345,19 @@ int build_groups(sdr_batch *h) {
    * ordered by mode so that the lanes of a warp run the same oscillator frequency and coefficient set (channel results
    * never depend on the grouping). */
   static const int order[2][5] = {{SDR_LSB, SDR_USB, SDR_CW_LSB, SDR_CW_USB, SDR_WSPR}, {SDR_AM, SDR_SAM, -1, -1, -1}};
-  std::vector<uint32_t> by_key[2][4][5];
+  std::vector<uint32_t> by_key[2][8][5];
   for (uint32_t c = 0; c < h->n_ch; c++) {
     const int m = h->sh[c].mode, cls = (m == SDR_AM || m == SDR_SAM) ? CLS_ENV : CLS_SSB;
     int mi = 0;
     for (int k = 0; k < 5; k++) if (order[cls][k] == m) mi = k;
-    by_key[cls][lay_feat_of(h->h_cfg[c].flags)][mi].push_back(c);
+    uint32_t f = lay_feat_of(h->h_cfg[c].flags);
+#ifndef SDR_HANDOVER
+    if (m == SDR_SAM) f |= LF_SAM; /* SAM channels get groups (and a bucket) of their own: no AM lane among them */
+#endif
+    by_key[cls][f][mi].push_back(c);
   }
   for (int cls = 0; cls < 2; cls++) {
-    for (uint32_t feat = 0; feat < 4; feat++) {
+    for (uint32_t feat = 0; feat < 8; feat++) {
       Bucket b; b.first = (uint32_t)h->h_groups.size();
       SdrGroup g; int fill = 0;
       auto flush = [&]() {

@@ -31,8 +31,11 @@ enum {
   ST_AUD = 9, ST_AGC = 10, ST_OUT = 11, ST_ENVL = 12, ST_NBO = 13
 };
 
-/* bucket features */
-enum { LF_NB = 1u, LF_ALS = 2u };
+/* bucket features.  LF_SAM: an ENV bucket whose groups hold SAM channels only (no AM lane): the AGC never needs the
+ * block's carrier level (C:408-409 is AM-mode only), and the envelope path runs only for blocks the PLL ends unlocked
+ * (C:130-132), i.e. rarely -- so on short tiles its four stages share one warp, and input and output another: 7 warps
+ * instead of 11, three groups per SM. */
+enum { LF_NB = 1u, LF_ALS = 2u, LF_SAM = 4u };
 
 /* The plan of every 32-sample-tile launch is the same (whatever optional stages the bucket has): offsets and ring depths
  * are compile-time constants of the 32-sample kernel, and a group with all stages fills the SM's shared memory. */
@@ -150,7 +153,7 @@ static inline void lay_rules(SdrLay *L) {
     lay_dep(L, ST_MAG, ST_AGC, 0, -L->na);
     lay_dep(L, ST_AUD, ST_MAG, 0, 0);
     lay_dep(L, ST_AGC, ST_AUD, 0, 0);
-    lay_dep(L, ST_AGC, ST_MAG, 1, 0);
+    if (!(L->feat & LF_SAM)) lay_dep(L, ST_AGC, ST_MAG, 1, 0);
   }
   lay_dep(L, ST_AGC, ST_OUT, 0, -(L->nc - back_c));
   lay_dep(L, ST_OUT, ST_AGC, 0, 0);
@@ -168,7 +171,16 @@ static inline int lay_check(const SdrLay *L) {
     for (int i = 0; i < SDR_MAX_DEPS && L->deps[s][i].stage >= 0; i++) {
       const SdrDep d = L->deps[s][i];
       const int k = d.kind ? L->tpb - 1 : d.k; /* worst case of (t | (tpb - 1)) - t */
-      if (!(k + L->delay[d.stage] < L->delay[s])) return 2;
+      if (!(k + L->delay[d.stage] < L->delay[s])) {
+        /* the same step is in order only inside one warp's program, when the stage waited for comes first */
+        int ok = 0;
+        for (int w = 0; w < L->n_warps && !ok; w++) {
+          int ps = -1, pd = -1;
+          for (int i = 0; i < 4 && L->prog[w][i] != 0xFF; i++) { if (L->prog[w][i] == s) ps = i; if (L->bar_of[L->prog[w][i]] == d.stage) pd = i > pd ? i : pd; }
+          if (ps >= 0 && pd >= 0 && pd < ps && k + L->delay[d.stage] == L->delay[s]) ok = 1;
+        }
+        if (!ok) return 2;
+      }
       if (d.k < -(SDR_BAR_W - 2)) return 3;
     }
   }
@@ -201,6 +213,10 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
     d[ST_PLL] = (int8_t)(d[ST_IFI] + 1); d[ST_NCO2] = (int8_t)(d[ST_PLL] + tpb); d[ST_IMGI] = d[ST_IMGQ] = (int8_t)(d[ST_NCO2] + 1);
     d[ST_MAG] = (int8_t)(d[ST_NCO2] + 2); d[ST_AUD] = (int8_t)(d[ST_MAG] + 1); d[ST_AGC] = (int8_t)(d[ST_MAG] + tpb);
   }
+  /* SAM-only ENV bucket on short tiles: the four envelope stages run one after the other in one warp at the same step (their
+   * work ring needs one slot), and the AGC follows the audio filter directly */
+  const int merged = cls == CLS_ENV && (feat & LF_SAM) && !(feat & (LF_NB | LF_ALS)) && T != 32;
+  if (merged) { d[ST_IMGI] = d[ST_IMGQ] = d[ST_MAG] = d[ST_NCO2]; d[ST_AUD] = (int8_t)(d[ST_NCO2] + 1); d[ST_AGC] = (int8_t)(d[ST_AUD] + 1); }
   L->active[ST_AUD] = L->active[ST_AGC] = L->active[ST_OUT] = 1; d[ST_OUT] = (int8_t)(d[ST_AGC] + 1);
   for (int s = 0; s < SDR_STAGES; s++) if (L->active[s] && d[s] > L->dmax) L->dmax = d[s];
   /* barrier groups */
@@ -236,7 +252,7 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   L->nr = d[x0] + 1;
   L->nc = back_c + 2;
   if (cls == CLS_SSB) { L->hq_tiles = back_q + 2; L->ni = tpb + 2; L->na = 3; }
-  else { L->nz = tpb + 1; L->nz2 = 3; L->na = tpb + 1; }
+  else { L->nz = tpb + 1; L->nz2 = merged ? 1 : 3; L->na = merged ? 3 : tpb + 1; }
   /* fixed part */
   int o = 0;
   L->o_sine = o; o += 1152;
@@ -285,8 +301,19 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   /* warps: one per active stage, in stage order until a measured placement is supplied (lay_place).  The 32-sample plan
    * keeps all 14 warps whatever the bucket -- stages it does not need only keep step with the others -- so that the one
    * measured placement of stages on SM sub-partitions serves every bucket. */
+  memset(L->prog, 0xFF, sizeof L->prog);
   L->n_warps = 0;
-  for (int s = 0; s < SDR_STAGES; s++) if (L->active[s] || T == 32) L->stage_of_warp[L->n_warps++] = (uint8_t)s;
+  if (merged) {
+    static const uint8_t P[7][4] = {{ST_IN, ST_OUT, 0xFF, 0xFF}, {ST_IFI, 0xFF, 0xFF, 0xFF}, {ST_IFQ, 0xFF, 0xFF, 0xFF}, {ST_PLL, 0xFF, 0xFF, 0xFF},
+                                    {ST_NCO2, ST_IMGI, ST_IMGQ, ST_MAG}, {ST_AUD, 0xFF, 0xFF, 0xFF}, {ST_AGC, 0xFF, 0xFF, 0xFF}};
+    /* placement: warp id % 4 = SM sub-partition; the PLL warp (the group's latency chain) gets the highest id of its own */
+    static const uint8_t order[7] = {1, 2, 0, 5, 4, 6, 3};
+    for (int w = 0; w < 7; w++) memcpy(L->prog[w], P[order[w]], 4);
+    L->n_warps = 7;
+  } else {
+    for (int s = 0; s < SDR_STAGES; s++) if (L->active[s] || T == 32) L->prog[L->n_warps++][0] = (uint8_t)s;
+  }
+  for (int w = 0; w < L->n_warps; w++) L->stage_of_warp[w] = L->prog[w][0];
   lay_rules(L);
   return lay_check(L);
 }
@@ -298,7 +325,8 @@ static inline int lay_place(SdrLay *L, unsigned long long map) {
   for (int s = 0; s < SDR_STAGES; s++) if (L->active[s] || L->T == 32) want |= 1u << s;
   for (int w = 0; w < L->n_warps; w++) seen |= 1u << ((map >> (4 * w)) & 15);
   if (seen != want) return 1;
-  for (int w = 0; w < L->n_warps; w++) L->stage_of_warp[w] = (uint8_t)((map >> (4 * w)) & 15);
+  for (int w = 0; w < L->n_warps; w++) if (L->prog[w][1] != 0xFF) return 1; /* merged programs keep their own placement */
+  for (int w = 0; w < L->n_warps; w++) { L->stage_of_warp[w] = (uint8_t)((map >> (4 * w)) & 15); L->prog[w][0] = L->stage_of_warp[w]; }
   return 0;
 }
 

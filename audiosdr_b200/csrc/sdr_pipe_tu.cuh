@@ -92,6 +92,55 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
     if (x.Y->stage_of_warp[0] == stage) { row[14] += (unsigned long long)(clock64() - t_begin); row[15] += (unsigned long long)(t_loaded - x.t0); }
   }
 }
+
+/* A warp that runs several stages per step (merged plans, sdr_lay.h): `step(s)` works through the warp's program. */
+template <class Step>
+__device__ __forceinline__ void lockstep_loop(const Ctx &x, Step step) {
+  cta_barrier();
+  const uint32_t steps = x.L->n_tiles + (uint32_t)x.Y->dmax;
+#pragma unroll 1
+  for (uint32_t s = 0; s < steps; s++) { step(s); cta_barrier(); }
+}
+__device__ __forceinline__ bool tile_at(const Ctx &x, int stage, uint32_t s, uint32_t &tau) {
+  const long long t = (long long)s - x.Y->delay[stage];
+  tau = (uint32_t)t;
+  return t >= 0 && t < (long long)x.L->n_tiles;
+}
+
+/* input and output of a group in one warp: both are short, memory-bound stages */
+__device__ __forceinline__ void run_in_out(const Ctx &x, int lane) {
+  RoleIn rin; RoleOut rout; rin.load(x, lane); rout.load(x, lane);
+  Slots k_in, k_out; k_in.reset(); k_out.reset();
+  lockstep_loop(x, [&](uint32_t s) {
+    uint32_t t;
+    if (tile_at(x, ST_IN, s, t)) { x.k = k_in; rin.step_a(x, lane, t); __syncwarp(); rin.step_b(x, lane, t); k_in.advance(x); }
+    if (tile_at(x, ST_OUT, s, t)) { x.k = k_out; rout.step_a(x, lane, t); __syncwarp(); rout.step_b(x, lane, t); __syncwarp(); k_out.advance(x); }
+  });
+  rin.save(x, lane);
+  x.k = k_out; rout.save(x, lane);
+}
+
+/* the envelope path of a SAM-only group in one warp (C:132-143): AM-phase NCO, image low-pass on both rails, magnitude.  It
+ * computes only for blocks the PLL ended unlocked; the image filters' delay lines stay in the channel state between tiles
+ * (loaded and stored around a tile that needs them), so the warp holds one cascade at a time. */
+__device__ __forceinline__ void run_envelope_path(const Ctx &x, int lane) {
+  RoleNco2 n2; RoleMag mg; n2.load(x, lane); mg.load(x, lane);
+  x.k.reset();
+  lockstep_loop(x, [&](uint32_t s) {
+    uint32_t t;
+    if (!tile_at(x, ST_NCO2, s, t)) return;
+    n2.step(x, lane, t);
+    __syncwarp();
+    if (__any_sync(0xffffffffu, n2.cid >= 0 && env_flag(x, lane, t) != 0)) {
+#pragma unroll 1
+      for (int rail = 0; rail < 2; rail++) { RoleBiquad r; r.load(x, lane, 2, rail); r.step(x, lane, t); r.save(x); }
+    }
+    __syncwarp();
+    mg.step(x, lane, t);
+    x.k.advance(x);
+  });
+  n2.save(x); mg.save(x);
+}
 #else
 template <class Body>
 __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body) {
@@ -147,6 +196,12 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
 __device__ __forceinline__ void run_stage(const Ctx &x, int stage, int lane) {
   const bool ssb = x.Y->cls == CLS_SSB;
   if (!x.Y->active[stage]) { pipeline_loop(x, stage, [&](uint32_t) {}); return; } /* a stage this bucket does not have: keeps step only */
+#if defined(SDR_LOCKSTEP) && SDR_FIXED_T != 32
+  if (x.Y->prog[threadIdx.x >> 5][1] != 0xFF) { /* merged plan: this warp runs several stages per step */
+    if (stage == ST_IN) run_in_out(x, lane); else run_envelope_path(x, lane);
+    return;
+  }
+#endif
   /* every 4-section cascade of the chain (IF rails, audio band-pass, AM image rails) runs through this one site */
   const bool is_if = stage == ST_IFI || stage == ST_IFQ, is_aud = stage == ST_AUD, is_img = !ssb && (stage == ST_IMGI || stage == ST_IMGQ);
   if (is_if || is_aud || is_img) {

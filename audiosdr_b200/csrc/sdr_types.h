@@ -114,7 +114,9 @@ typedef struct {
   int32_t ins_row;                   /* floats per row of the input / output staging areas */
   int32_t o_sine, o_lut, o_ncot, o_cid, o_bar, o_flags, o_carr, o_nbs, o_mask, o_alsc, o_ins, o_outs, o_r, o_hq, o_hi, o_z, o_z2, o_a, o_c;
   int32_t smem_bytes, n_warps, dmax, error;
-  uint8_t stage_of_warp[16];         /* physical warp -> stage id */
+  uint8_t stage_of_warp[16];         /* physical warp -> (first) stage id */
+  uint8_t prog[16][4];               /* physical warp -> the stages it runs each step, in this order (0xFF ends the list): one stage per warp
+                                        except in the plans that merge light stages into one warp (sdr_lay.h, LF_SAM) */
   uint8_t active[16];                /* stage id -> runs in this launch */
   uint8_t bar_of[16];                /* stage id -> the stage whose barriers it signals: stages that always hand over together (the two IF rails,
                                         the Hilbert warps, the two image rails) share one barrier per tile, completed by all their arrivals */
@@ -147,6 +149,7 @@ typedef struct {
  * scheduler) for the launches that run all 14 stages; SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */
 #define SDR_MAP_SSB_DEFAULT 0x3BADC548961720ull
 #define SDR_MAP_ENV_DEFAULT 0xA0D459B1328C67ull
+#define SDR_MAP_ENV_LEAN_DEFAULT 0x52980364BA7ull /* the 11-warp ENV plan on 16-sample tiles, two groups per SM (tools/map_search.py --cls envlean) */
 
 #define SDR_PROF_SLOTS 64 /* [0..15] busy cycles per stage, [16..31] cycles waiting for other stages, [32] CTA cycles, [33] prologue (diagnostics twin only) */
 

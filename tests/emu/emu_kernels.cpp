@@ -132,17 +132,18 @@ int run_group(const SdrLaunch &L, const SdrGroup &G) {
     const char *r = getenv("SDR_EMU_REVERSE");
     const bool reverse = r && r[0] == '1';
     for (uint32_t s = 0; s < n + (uint32_t)Y.dmax; s++) {
-      /* all stages of a step see the state the previous step left: collect first, then run */
-      std::vector<int> now;
-      for (int st = 0; st < SDR_STAGES; st++) {
-        if (!Y.active[st]) continue;
-        const long long tau = (long long)s - Y.delay[st];
-        if (tau < 0 || tau >= (long long)n) continue;
-        if (done[st] != tau || !runnable(Y, done, st, n)) { fprintf(stderr, "[emu] lock-step schedule violates a hand-over rule: stage %d tile %lld\n", st, tau); return 1; }
-        now.push_back(st);
+      /* the warps of a step in either order; the stages one warp runs in a step (its program) always in program order */
+      for (int wi = 0; wi < Y.n_warps; wi++) {
+        const int w = reverse ? Y.n_warps - 1 - wi : wi;
+        for (int i = 0; i < 4 && Y.prog[w][i] != 0xFF; i++) {
+          const int st = Y.prog[w][i];
+          if (!Y.active[st]) continue;
+          const long long tau = (long long)s - Y.delay[st];
+          if (tau < 0 || tau >= (long long)n) continue;
+          if (done[st] != tau || !runnable(Y, done, st, n)) { fprintf(stderr, "[emu] lock-step schedule violates a hand-over rule: stage %d tile %lld\n", st, tau); return 1; }
+          run_tile(st);
+        }
       }
-      if (reverse) std::reverse(now.begin(), now.end());
-      for (int st : now) run_tile(st);
     }
   } else {
     uint64_t rng = 0x9E3779B97F4A7C15ull;

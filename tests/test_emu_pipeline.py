@@ -194,10 +194,13 @@ def test_every_hand_over_rule_is_needed(oracle, emu_lib, monkeypatch):
     assert [r for r in missed if r < 21] == [], "schedules did not notice the missing rule(s) %s" % missed
 
 
-def test_emulated_sam_driven_out_of_lock_and_back(oracle, emu_lib, monkeypatch):
+@pytest.mark.parametrize("plan", [None, (8, 3, 1), (16, 2, 0)])
+def test_emulated_sam_driven_out_of_lock_and_back(oracle, emu_lib, monkeypatch, plan):
     """SAM channels pushed out of the lock window and back (envelope fallback toggling per block, C:130-143), lean and
-    blanker-carrying ENV plans, under an adversarial schedule."""
+    blanker-carrying ENV plans, default and short-tile plans, under an adversarial schedule."""
     set_schedule(monkeypatch, "random:4/late")
+    if plan:
+        set_plan(monkeypatch, *plan)
     nch, nblk = 6, 400
     I, Q, ev = S.sam_lock_unlock_case(nch, nblk)
     o = oracle.run(I, Q, ev, threads=4)
@@ -251,14 +254,23 @@ def test_emulated_state_export_import_continues_bit_exact(oracle, emu_lib):
     assert harness.bits_equal(got, want), harness.describe_mismatch(got, want)
 
 
-@pytest.mark.parametrize("sched", ["lockstep", "consumers", "random:3/late"])
-@pytest.mark.parametrize("tile,ctas", [(16, 2), (8, 2), (16, 1)])
-@pytest.mark.parametrize("cfg,nch,nblk", [(1, 1, 24), (3, 6, 30), (5, 5, 30)])
-def test_emulated_short_tile_plans(oracle, emu_lib, monkeypatch, cfg, nch, nblk, tile, ctas, sched):
-    """Buckets without blanker and ALS can run 16- or 8-sample tiles in a fraction of the shared memory (several groups
-    per SM; the product picks 16-sample tiles for large ENV buckets): same bits for every tile length and ring budget."""
-    set_schedule(monkeypatch, sched)
+SHORT_PLANS = [(16, 2, 0), (8, 2, 0), (16, 1, 0), (8, 3, 1), (16, 2, 1)]  # tile length, groups per SM, SAM-only buckets on the merged 7-warp plan
+
+
+def set_plan(monkeypatch, tile, ctas, merge):
     monkeypatch.setenv("SDR_TILE_SSB", str(tile)); monkeypatch.setenv("SDR_TILE_ENV", str(tile)); monkeypatch.setenv("SDR_CTAS_PER_SM", str(ctas))
+    monkeypatch.setenv("SDR_NO_MERGE", "0" if merge else "1")
+
+
+@pytest.mark.parametrize("sched", ["lockstep", "lockstep-reversed", "consumers", "random:3/late"])
+@pytest.mark.parametrize("tile,ctas,merge", SHORT_PLANS)
+@pytest.mark.parametrize("cfg,nch,nblk", [(1, 1, 24), (3, 6, 30), (5, 5, 30)])
+def test_emulated_short_tile_plans(oracle, emu_lib, monkeypatch, cfg, nch, nblk, tile, ctas, merge, sched):
+    """Buckets without blanker and ALS can run 16- or 8-sample tiles in a fraction of the shared memory (several groups
+    per SM; the product picks them for large ENV buckets, SAM-only ones with the light stages merged into 7 warps): same
+    bits for every tile length, ring budget and warp program."""
+    set_schedule(monkeypatch, sched)
+    set_plan(monkeypatch, tile, ctas, merge)
     I, Q, ev = S.make(cfg, list(range(nch)), nblk)
     o = oracle.run(I, Q, ev, threads=4)
     a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(7, 1, 13), return_batch=True)

@@ -48,7 +48,13 @@ def test_cuda_wspr_120_seconds_drift(cuda_lib, oracle, dev):
     assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
 
 
-def test_cuda_sam_driven_out_of_lock_and_back(cuda_lib, oracle, dev):
+@pytest.mark.parametrize("plan", [None, (8, 3, 1), (16, 2, 0), (16, 2, 1)], ids=["default", "tile8-merged-x3", "tile16-x2", "tile16-merged-x2"])
+def test_cuda_sam_driven_out_of_lock_and_back(cuda_lib, oracle, dev, monkeypatch, plan):
+    """Lock -> unlock -> envelope fallback -> re-lock over 10 s, on the default plan and on the short-tile plans the product
+    picks for large ENV buckets (the blanker-carrying channels of the case stay on the 32-sample plan either way)."""
+    if plan:
+        from test_emu_pipeline import set_plan
+        set_plan(monkeypatch, *plan)
     nch, nblk = 12, S.BLOCKS_10S
     I, Q, ev = S.sam_lock_unlock_case(nch, nblk)
     o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)

@@ -94,6 +94,19 @@ def test_cuda_float32_planes_and_gains(cuda_lib, oracle, dev):
     assert_same(ai, oi["audio"])
 
 
+@pytest.mark.parametrize("tile,ctas,merge", [(16, 2, 0), (8, 2, 0), (8, 3, 1), (16, 2, 1)])
+@pytest.mark.parametrize("cfg,nch,nblk", [(1, 1, 60), (3, 70, 60), (5, 40, 60)])
+def test_cuda_short_tile_plans(cuda_lib, oracle, dev, monkeypatch, cfg, nch, nblk, tile, ctas, merge):
+    """The plans for buckets without blanker and ALS (16- / 8-sample tiles, several groups per SM, merged warps): same bits."""
+    from test_emu_pipeline import set_plan
+    set_plan(monkeypatch, tile, ctas, merge)
+    I, Q, ev = S.make(cfg, list(range(nch)), nblk)
+    o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
+    a, b = harness.run_batch(cuda_lib, I, Q, ev, chunks=(17, 1, 40), device=dev, return_batch=True)
+    assert_same(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+
+
 def test_cuda_lone_mode_switch(cuda_lib, oracle, dev):
     """setDemodMode as the only setter at a block boundary (same-class and SSB<->AM/SAM class changes)."""
     from test_emu_pipeline import lone_mode_switch_case
