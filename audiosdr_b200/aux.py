@@ -18,7 +18,8 @@ EXPORTS = ["sdr_preproc_create", "sdr_preproc_destroy", "sdr_preproc_set", "sdr_
            "sdr_preproc_process_host", "sdr_preproc_launch_count", "sdr_iqgen_create", "sdr_iqgen_destroy",
            "sdr_iqgen_set_gain_balance", "sdr_iqgen_process_device", "sdr_iqgen_process_host", "sdr_iqgen_launch_count",
            "sdr_grabber_create", "sdr_grabber_destroy", "sdr_grabber_process_device", "sdr_grabber_new_data_available",
-           "sdr_grabber_grab", "sdr_grabber_grab_device", "sdr_aux_last_error", "sdr_aux_version"]
+           "sdr_grabber_grab", "sdr_grabber_grab_device", "sdr_grabber_spectrum", "sdr_grabber_spectrum_device", "sdr_aux_last_error",
+           "sdr_aux_version"]
 
 
 class AuxError(RuntimeError):
@@ -66,6 +67,8 @@ def load_library(path=None):
     L.sdr_grabber_new_data_available.argtypes = [vp, u32]
     L.sdr_grabber_grab.argtypes = [vp, vp, u32, vp]
     L.sdr_grabber_grab_device.argtypes = [vp, vp, vp]
+    L.sdr_grabber_spectrum.argtypes = [vp, vp, u32, vp]
+    L.sdr_grabber_spectrum_device.argtypes = [vp, vp, u32, vp, vp]
     L.sdr_aux_last_error.restype = C.c_char_p
     L.sdr_aux_version.restype = C.c_char_p
     if path is None:
@@ -225,6 +228,26 @@ class GrabberBatch(_Base):
         if r < 0:
             self._check(r)
         return bool(r)
+
+    def spectrum(self, channels=None):
+        """float32 [n, 256]: power per bin of the 256-point FFT of each channel's snapshot (natural bin order), or None while
+        no snapshot is valid.  A view of the snapshot: the new-data flags stay as they are."""
+        p, n, keep = _sel(channels)
+        cnt = n if channels is not None else self.n_channels
+        out = np.empty((cnt, 256), np.float32)
+        r = self.L.sdr_grabber_spectrum(self.h, p, n, out.ctypes.data)
+        if r < 0:
+            self._check(r)
+        return out if r > 0 else None
+
+    def spectrum_device(self, power, stream=None):
+        """All channels into a CUDA float32 tensor [n_channels, 256]; returns False while no snapshot is valid."""
+        assert power.is_cuda and tuple(power.shape) == (self.n_channels, 256) and power.is_contiguous()
+        sp = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        r = self.L.sdr_grabber_spectrum_device(self.h, None, 0, power.data_ptr(), sp)
+        if r < 0:
+            self._check(r)
+        return r > 0
 
     def grab(self, channels=None):
         """int16 [n, 512] (re, im interleaved) or None while no pair of blocks has completed (the reference's grab() then

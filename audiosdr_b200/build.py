@@ -50,9 +50,13 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def needs_aux_build():
+    return not (os.path.exists(AUX_LIB) and all(os.path.getmtime(os.path.join(CSRC, d)) <= os.path.getmtime(AUX_LIB) for d in AUX_DEPS))
+
+
 def build_aux_library(force=False, verbose=False):
     """Builds audiosdr_b200/libsdr_aux.so (pre-processor + I/Q generator, include/sdr_aux.h); returns its path."""
-    if not force and os.path.exists(AUX_LIB) and all(os.path.getmtime(os.path.join(CSRC, d)) <= os.path.getmtime(AUX_LIB) for d in AUX_DEPS):
+    if not force and not needs_aux_build():
         return AUX_LIB
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "sdr_aux.cu"), "-o", AUX_LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -25,6 +25,7 @@
 
 __constant__ float c_iq_h[64];
 __constant__ float c_fft_tw[128];
+__constant__ float c_fft_tw256[256];
 
 /* ================================================================== I/Q generator ==== */
 #define IQ_SEG 4096
@@ -321,6 +322,9 @@ static int upload_tables() {
   memcpy(tw, AUX_FFT_TW, sizeof tw);
   CK(cudaMemcpyToSymbol(c_iq_h, h, sizeof h));
   CK(cudaMemcpyToSymbol(c_fft_tw, tw, sizeof tw));
+  float tw256[256];
+  memcpy(tw256, AUX_FFT_TW256, sizeof tw256);
+  CK(cudaMemcpyToSymbol(c_fft_tw256, tw256, sizeof tw256));
   return 0;
 }
 
@@ -560,6 +564,37 @@ extern "C" int sdr_iqgen_process_host(sdr_iqgen_t *h, const int16_t *X, size_t i
 
 extern "C" uint64_t sdr_iqgen_launch_count(const sdr_iqgen_t *h) { return h ? h->launches : 0; }
 
+/* Spectrum tap on the snapshots (the panadapter that consumes grab()): per channel the 256-point forward
+ * complex FFT of the snapshot's (re, im) int16 pairs taken as floats, then the power re^2 + im^2 of every bin in natural bin
+ * order.  One CTA = one channel, 128 threads = the 128 butterflies of a stage; the operation network is the radix-2
+ * decimation-in-frequency one of the oracle (oracle/aux_fft128.h, aux_cfft_forward with n = 256), one rounding per operation. */
+__global__ void __launch_bounds__(128) grab_spectrum_kernel(const int16_t *snap, const uint32_t *channels, float *power) {
+  __shared__ float2 buf[256];
+  const uint32_t ch = channels ? channels[blockIdx.x] : blockIdx.x;
+  const int t = threadIdx.x;
+  const int2 raw = reinterpret_cast<const int2 *>(snap + (size_t)ch * 512)[t]; /* samples 2t, 2t+1: (re, im, re, im) */
+  buf[2 * t] = make_float2((float)(int16_t)(raw.x & 0xFFFF), (float)(int16_t)(raw.x >> 16));
+  buf[2 * t + 1] = make_float2((float)(int16_t)(raw.y & 0xFFFF), (float)(int16_t)(raw.y >> 16));
+  __syncthreads();
+#pragma unroll 1
+  for (int half = 128; half >= 1; half >>= 1) {
+    const int step = 128 / half, j = t & (half - 1), ia = ((t / half) * 2 * half) + j, ib = ia + half;
+    const float2 a = buf[ia], b = buf[ib];
+    const float tr = a.x - b.x, ti = a.y - b.y;
+    const float wr = c_fft_tw256[2 * j * step], wi = c_fft_tw256[2 * j * step + 1];
+    const float p0 = tr * wr, p1 = ti * wi, p2 = tr * wi, p3 = ti * wr;
+    buf[ia] = make_float2(a.x + b.x, a.y + b.y);
+    buf[ib] = make_float2(p0 - p1, p2 + p3);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = t; k < 256; k += 128) {
+    const float2 v = buf[__brev((unsigned)k) >> 24]; /* 8-bit reversal: natural bin order */
+    const float a = v.x * v.x, b = v.y * v.y;
+    power[(size_t)blockIdx.x * 256 + k] = a + b;
+  }
+}
+
 /* ------------------------------------------------------------------ grabber ---- */
 struct sdr_grabber {
   uint32_t n = 0; int device = 0;
@@ -633,6 +668,43 @@ extern "C" int sdr_grabber_grab_device(sdr_grabber_t *h, int16_t *dest, void *cu
   if (h->valid) CK(cudaMemcpyAsync(dest, h->outb, 1024 * (size_t)h->n, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
   std::fill(h->fresh.begin(), h->fresh.end(), (uint8_t)0);
   return h->valid ? 1 : 0;
+}
+
+/* power[i*256 + k] = |FFT256(snapshot of channel i)|^2[k], device memory, for the listed channels (device array, NULL: all);
+ * returns 0 when no snapshot is valid yet (nothing written), 1 when written.  Does not touch the new-data flags. */
+extern "C" int sdr_grabber_spectrum_device(sdr_grabber_t *h, const uint32_t *d_channels, uint32_t n, float *d_power, void *cuda_stream) {
+  if (!h || !d_power) return fail(SDR_AUX_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->device));
+  if (!h->valid) return 0;
+  const uint32_t cnt = d_channels ? n : h->n;
+  if (cnt == 0) return 1;
+  grab_spectrum_kernel<<<cnt, 128, 0, (cudaStream_t)cuda_stream>>>(h->outb, d_channels, d_power);
+  CK(cudaGetLastError());
+  return 1;
+}
+
+/* the same to HOST memory for the listed channels (NULL: all) */
+extern "C" int sdr_grabber_spectrum(sdr_grabber_t *h, const uint32_t *channels, uint32_t n, float *power) {
+  if (!h || !power) return fail(SDR_AUX_EINVAL, "bad arguments");
+  const uint32_t cnt = channels ? n : h->n;
+  for (uint32_t i = 0; i < cnt; i++) if ((channels ? channels[i] : i) >= h->n) return fail(SDR_AUX_EINVAL, "channel out of range");
+  CK(cudaSetDevice(h->device));
+  if (!h->valid) return 0;
+  if (cnt == 0) return 0;
+  uint32_t *d_ch = nullptr; float *d_p = nullptr;
+  int rc = 0;
+  do {
+    if (cudaMalloc(&d_p, (size_t)cnt * 1024) != cudaSuccess) { rc = fail(SDR_AUX_ENOMEM, "cudaMalloc failed"); break; }
+    if (channels) {
+      if (cudaMalloc(&d_ch, (size_t)cnt * 4) != cudaSuccess) { rc = fail(SDR_AUX_ENOMEM, "cudaMalloc failed"); break; }
+      if (cudaMemcpy(d_ch, channels, (size_t)cnt * 4, cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(SDR_AUX_ECUDA, "copy failed"); break; }
+    }
+    grab_spectrum_kernel<<<cnt, 128>>>(h->outb, d_ch, d_p);
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpy(power, d_p, (size_t)cnt * 1024, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail(SDR_AUX_ECUDA, "spectrum kernel failed"); break; }
+    rc = (int)cnt;
+  } while (0);
+  cudaFree(d_ch); cudaFree(d_p);
+  return rc;
 }
 
 extern "C" const char *sdr_aux_last_error(void) { return g_err.c_str(); }

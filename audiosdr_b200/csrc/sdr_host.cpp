@@ -323,7 +323,15 @@ int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
   if (env_int("SDR_NO_MERGE", 0)) feat &= ~(uint32_t)LF_SAM;
   const int slack = env_int("SDR_SLACK", 0); /* extra ring slots only matter to the hand-over build (-DSDR_HANDOVER) */
   const int budget = (233472 - 1024 * ctas) / ctas; /* an SM has 228 KB, each resident CTA costs 1 KB of it */
-  int rc = lay_build(&b.lay, cls, feat, T, budget > 232448 ? 232448 : budget, slack);
+  /* experiments: input requests ahead (SDR_IN_DEPTH), order of the merged plan's seven warp programs (SDR_MAP_ENV_MERGED: a
+   * permutation of 0..6 as hex digits, warp 0 first; programs: 0 in+out, 1 IF-I, 2 IF-Q, 3 PLL, 4 envelope path, 5 audio, 6 AGC) */
+  uint8_t mo[7]; const uint8_t *merged_order = nullptr;
+  if (const char *e = getenv("SDR_MAP_ENV_MERGED")) {
+    unsigned seen = 0;
+    if (strlen(e) == 7) for (int w = 0; w < 7; w++) { mo[w] = (uint8_t)(e[w] - '0'); if (mo[w] < 7) seen |= 1u << mo[w]; }
+    if (seen == 0x7Fu) merged_order = mo;
+  }
+  int rc = lay_build_ex(&b.lay, cls, feat, T, budget > 232448 ? 232448 : budget, slack, env_int("SDR_IN_DEPTH", 0), merged_order);
   if (rc) rc = lay_build(&b.lay, cls, feat, 32, 232448, 0);
   if (rc) return rc;
   /* measured placements */

@@ -191,7 +191,7 @@ static inline int lay_check(const SdrLay *L) {
 }
 
 /* slack: extra ring slots beyond the lock-step minimum, each ring at most `max_slack`, as long as `budget` bytes allow */
-static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget, int max_slack) {
+static inline int lay_build_ex(SdrLay *L, int cls, uint32_t feat, int T, int budget, int max_slack, int in_depth_override, const uint8_t *merged_order) {
   memset(L, 0, sizeof *L);
   if (T != 32 && T != 16 && T != 8) return 1;
   if ((feat & (LF_NB | LF_ALS)) && T != 32) return 1; /* the blanker scan and the ALS passes are written for 32-sample tiles */
@@ -257,7 +257,7 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   int o = 0;
   L->o_sine = o; o += 1152;
   L->o_lut = o; o += lay_align(SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE * 4, 128);
-  L->o_ncot = o; o += 256;
+  if (cls == CLS_SSB) { L->o_ncot = o; o += 256; } /* the shared NCO table of an SSB group */
   L->o_cid = o; o += 128;
   L->o_bar = o; o += LAY32_BAR_BYTES; /* hand-over barriers: only the -DSDR_HANDOVER build has them */
   if (cls == CLS_ENV) { L->o_flags = o; o += 8 * SDR_LANES * 4; L->o_carr = o; o += 8 * SDR_LANES * 4; }
@@ -265,6 +265,7 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   if (als) { L->o_alsc = o; o += 128 * SDR_LANES * 4; }
   L->ins_row = T + 4; /* staging rows padded by 16 bytes: a lane reading its own row with 16-byte loads is bank-conflict free */
   L->in_depth = T == 32 ? 1 : (T == 16 ? 2 : 4); /* the request has to cover the DRAM latency: about one 32-sample tile time */
+  if (in_depth_override > 0 && in_depth_override <= 4) L->in_depth = in_depth_override;
   L->o_ins = o; o += L->in_depth * 2 * SDR_LANES * L->ins_row * 4;
   L->o_outs = o; o += SDR_LANES * L->ins_row * 4;
   const int fixed = o;
@@ -307,7 +308,8 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
     static const uint8_t P[7][4] = {{ST_IN, ST_OUT, 0xFF, 0xFF}, {ST_IFI, 0xFF, 0xFF, 0xFF}, {ST_IFQ, 0xFF, 0xFF, 0xFF}, {ST_PLL, 0xFF, 0xFF, 0xFF},
                                     {ST_NCO2, ST_IMGI, ST_IMGQ, ST_MAG}, {ST_AUD, 0xFF, 0xFF, 0xFF}, {ST_AGC, 0xFF, 0xFF, 0xFF}};
     /* placement: warp id % 4 = SM sub-partition; the PLL warp (the group's latency chain) gets the highest id of its own */
-    static const uint8_t order[7] = {1, 2, 0, 5, 4, 6, 3};
+    static const uint8_t order_default[7] = {1, 2, 0, 5, 4, 6, 3};
+    const uint8_t *order = merged_order ? merged_order : order_default;
     for (int w = 0; w < 7; w++) memcpy(L->prog[w], P[order[w]], 4);
     L->n_warps = 7;
   } else {
@@ -316,6 +318,10 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   for (int w = 0; w < L->n_warps; w++) L->stage_of_warp[w] = L->prog[w][0];
   lay_rules(L);
   return lay_check(L);
+}
+
+static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget, int max_slack) {
+  return lay_build_ex(L, cls, feat, T, budget, max_slack, 0, (const uint8_t *)0);
 }
 
 /* placement: `map` = stage id of physical warp w in bits 4w..4w+3 (as many nibbles as the launch has warps); ignored unless it

@@ -176,6 +176,57 @@ def bench_path(path, args):
     h.close()
 
 
+def bench_spectrum(args):
+    """Spectrum tap on the grabber's snapshots: one 256-point complex FFT + power per channel and launch."""
+    import torch
+    from audiosdr_b200 import aux
+    from oracle import aux_lib as A
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.current_stream()
+    nch = 65536
+    g = torch.Generator(device=dev); g.manual_seed(99)
+    I = (torch.randn((nch, 256), generator=g, device=dev) * 3000.0).round().clamp(-32768, 32767).to(torch.int16)
+    Q = (torch.randn((nch, 256), generator=g, device=dev) * 3000.0).round().clamp(-32768, 32767).to(torch.int16)
+    t = torch.arange(256, device=dev, dtype=torch.float32)
+    I += (8000.0 * torch.cos(2 * np.pi * 37.0 / 256.0 * t)).round().to(torch.int16)[None, :]
+    Q += (8000.0 * torch.sin(2 * np.pi * 37.0 / 256.0 * t)).round().to(torch.int16)[None, :]
+    h = aux.GrabberBatch(nch)
+    h.process(I, Q, n_blocks=2, stream=stream)
+    power = torch.empty((nch, 256), dtype=torch.float32, device=dev)
+    fn = lambda: h.spectrum_device(power, stream=stream)
+    assert fn()
+    torch.cuda.synchronize()
+    pick = [0, 1, 777, 40000, nch - 1]
+    snap = h.grab(pick)
+    want = A.grab_spectrum(snap)
+    got = power[pick].cpu().numpy()
+    parity = dict(channels=len(pick), bins=int(want.size), bit_exact=bool(np.array_equal(got.view(np.uint32), want.view(np.uint32))),
+                  peak_bin=int(np.argmax(got[0])))
+    total_ms, per = time_steps(fn, args.steps, args.warmup, stream)
+    launch_s = float(np.mean(per)) * 1e-3
+    hbm, hbm_src = measured_hbm()
+    ach = 2048.0 * nch / launch_s / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        sn = np.ascontiguousarray(np.tile(snap, (200, 1)))
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < min(args.cpu_seconds, 3.0):
+            A.grab_spectrum(sn); reps += 1
+        dt = time.perf_counter() - t0
+        cpu = dict(value=reps * sn.shape[0] * 256 / dt / 1e6, unit=UNIT, cores=1, kind="port", sample="%d snapshots x %d passes through the oracle's FFT on one core" % (sn.shape[0], reps))
+    line = dict(path="grabber_spectrum", metric="channel_samples_per_s", value=256.0 * nch / launch_s / 1e6, unit=UNIT, spectra_per_s=nch / launch_s,
+                n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="grabber spectrum tap: %d channels, one 256-point complex FFT + power per channel and launch" % nch, channels_per_gpu=nch),
+                gpu_launches=args.steps,
+                roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, peak_source=hbm_src, kernel="grab_spectrum_kernel",
+                              algorithmic_bytes_per_spectrum=2048.0),
+                cpu_baseline=cpu, parity=parity, per_launch_ms=dict(mean=float(np.mean(per)), min=float(np.min(per)), max=float(np.max(per))))
+    print(json.dumps(line), flush=True)
+    h.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--path", default="all")
@@ -187,8 +238,11 @@ def main():
     args = ap.parse_args()
     from audiosdr_b200 import build
     build.build_aux_library()
-    for p in (["iqgen", "preproc_static", "preproc_detect"] if args.path == "all" else [args.path]):
-        bench_path(p, args)
+    for p in (["iqgen", "preproc_static", "preproc_detect", "grabber_spectrum"] if args.path == "all" else [args.path]):
+        if p == "grabber_spectrum":
+            bench_spectrum(args)
+        else:
+            bench_path(p, args)
 
 
 if __name__ == "__main__":

@@ -92,6 +92,8 @@ class GrabberBatch {
   bool newDataAvailable(uint32_t c) { const int r = sdr_grabber_new_data_available(h_, c); if (r < 0) check(r, "sdr_grabber_new_data_available"); return r != 0; }
   /* grab(destination) of one channel: 512 int16 to host memory; false (destination untouched) before the first complete pair */
   bool grab(uint32_t c, int16_t *destination) { const int r = sdr_grabber_grab(h_, &c, 1, destination); if (r < 0) check(r, "sdr_grabber_grab"); return r > 0; }
+  /* spectrum tap: power[256] of the 256-point FFT of channel c's snapshot (natural bin order); false before the first complete pair */
+  bool spectrum(uint32_t c, float *power) { const int r = sdr_grabber_spectrum(h_, &c, 1, power); if (r < 0) check(r, "sdr_grabber_spectrum"); return r > 0; }
 
  private:
   static void check(int rc, const char *what) {

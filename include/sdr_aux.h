@@ -87,6 +87,15 @@ int sdr_grabber_grab(sdr_grabber_t *h, const uint32_t *channels, uint32_t n, int
 /* all channels, device to device: dest[n_channels][512]; returns 0 when nothing was valid yet, 1 when written */
 int sdr_grabber_grab_device(sdr_grabber_t *h, int16_t *dest, void *cuda_stream);
 
+/* Spectrum tap on the snapshots -- what the consumer of grab() does with them (the sketch's panadapter / S-meter; not part
+ * of the library classes): the 256-point forward complex FFT of a channel's snapshot, samples taken as
+ * floats (re, im) = (float)int16, and the power re^2 + im^2 per bin, natural bin order (bin k = k * 44100/256 Hz, bins 128..255
+ * = negative frequencies).  power[i*256 + k] for the i-th listed channel (NULL: all channels).  Returns the number of
+ * channels written (host form) / 1 (device form), 0 while no snapshot is valid yet, negative on error; the new-data flags
+ * are left alone (a spectrum is a view of the snapshot, not a grab()). */
+int sdr_grabber_spectrum(sdr_grabber_t *h, const uint32_t *channels, uint32_t n, float *power);
+int sdr_grabber_spectrum_device(sdr_grabber_t *h, const uint32_t *d_channels, uint32_t n, float *d_power, void *cuda_stream);
+
 const char *sdr_aux_last_error(void);
 const char *sdr_aux_version(void);
 

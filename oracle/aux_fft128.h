@@ -55,6 +55,36 @@ static inline void aux_cfft128_forward(float *buf) {
   }
 }
 
+/* the same network for n = 256 (spectrum tap on the grabber's snapshot, sdr_grabber_spectrum): in place, natural order */
+static inline float aux_tw256(int i) { float f; memcpy(&f, &AUX_FFT_TW256[i], 4); return f; }
+static inline void aux_cfft256_forward(float *buf) {
+  for (int half = 128; half >= 1; half >>= 1) {
+    const int step = 128 / half;
+    for (int base = 0; base < 256; base += 2 * half) {
+      for (int j = 0; j < half; j++) {
+        float *a = buf + 2 * (base + j), *b = buf + 2 * (base + j + half);
+        const float ar = a[0], ai = a[1], br = b[0], bi = b[1];
+        const float tr = ar - br, ti = ai - bi;
+        const float wr = aux_tw256(2 * j * step), wi = aux_tw256(2 * j * step + 1);
+        a[0] = ar + br;
+        a[1] = ai + bi;
+        const float p0 = tr * wr, p1 = ti * wi, p2 = tr * wi, p3 = ti * wr;
+        b[0] = p0 - p1;
+        b[1] = p2 + p3;
+      }
+    }
+  }
+  for (int i = 0; i < 256; i++) { /* 8-bit reversal */
+    int r = 0;
+    for (int k = 0; k < 8; k++) r |= ((i >> k) & 1) << (7 - k);
+    if (r > i) {
+      float t0 = buf[2 * i], t1 = buf[2 * i + 1];
+      buf[2 * i] = buf[2 * r]; buf[2 * i + 1] = buf[2 * r + 1];
+      buf[2 * r] = t0; buf[2 * r + 1] = t1;
+    }
+  }
+}
+
 /* dst[i] = re^2 + im^2, two products and one sum in float32; dst may be src (arm_cmplx_mag_squared_f32 semantics) */
 static inline void aux_cmplx_mag_squared(const float *src, float *dst, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) {

@@ -34,6 +34,8 @@ def lib():
         _lib.ora_aux_power128.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.ora_grab_run.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.ora_grab_run.restype = None
+        _lib.ora_grab_spectrum.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.ora_grab_spectrum.restype = None
     return _lib
 
 
@@ -70,6 +72,14 @@ def grab_run(I, Q):
     out = np.empty((nch, 512), np.int32); flags = np.empty((nch, 2), np.int32)
     lib().ora_grab_run(nch, ns // N_BLOCK, I.ctypes.data, Q.ctypes.data, out.ctypes.data, flags.ctypes.data)
     return out, flags
+
+
+def grab_spectrum(snap):
+    """Power spectra float32 [C, 256] of snapshots int16 [C, 512] (interleaved re, im): the oracle of sdr_grabber_spectrum."""
+    snap = np.ascontiguousarray(snap, np.int16)
+    out = np.empty((snap.shape[0], 256), np.float32)
+    lib().ora_grab_spectrum(snap.shape[0], snap.ctypes.data, out.ctypes.data)
+    return out
 
 
 def ref_grab_run(I, Q, jobs=8):

@@ -219,6 +219,19 @@ void ora_grab_run(uint32_t n_channels, uint32_t n_blocks, const int16_t *I, cons
   }
 }
 
+/* Spectrum tap on grabber snapshots (the consumer of grab(): the sketch's panadapter, not library code -- SURVEY 8f row 3):
+ * snap[c][512] interleaved (re, im) int16 -> power[c][256] = |FFT256|^2, samples taken as (float)int16, natural bin order.
+ * PARITY UNPINNED against the sketch (its code is not in the reference tree; CMSIS arm_cfft_f32 is restated, see aux_fft128.h);
+ * pinned against the mathematical DFT in tests/test_aux_oracle.py and bit for bit against the CUDA kernel. */
+void ora_grab_spectrum(uint32_t n_channels, const int16_t *snap, float *power) {
+  for (uint32_t c = 0; c < n_channels; c++) {
+    float buf[512];
+    for (int i = 0; i < 512; i++) buf[i] = (float)snap[(size_t)c * 512 + i];
+    aux_cfft256_forward(buf);
+    aux_cmplx_mag_squared(buf, power + (size_t)c * 256, 256);
+  }
+}
+
 /* natural-order power spectrum of one block as the detector sees it (for the float64-DFT decision test) */
 void ora_aux_power128(const int16_t *I, const int16_t *Q, float *power) {
   float buf[256];

@@ -105,6 +105,23 @@ def test_grabber_oracle_matches_reference_binary():
             assert np.array_equal(o[:, 0::2], I[:, (last - 2) * 128: last * 128]) and np.array_equal(o[:, 1::2], Q[:, (last - 2) * 128: last * 128])
 
 
+def test_spectrum_oracle_is_the_dft():
+    """The spectrum tap's oracle (radix-2 network in float32, oracle/aux_fft128.h) against the float64 DFT of numpy: the
+    restatement is the mathematically defined transform up to float32 rounding, bins in natural order."""
+    rng = np.random.default_rng(11)
+    snap = rng.integers(-30000, 30000, (16, 512)).astype(np.int16)
+    t = np.arange(256)
+    snap[0, 0::2] = np.round(20000 * np.cos(2 * np.pi * 5 * t / 256)); snap[0, 1::2] = np.round(20000 * np.sin(2 * np.pi * 5 * t / 256))      # +5 bins
+    snap[1, 0::2] = np.round(20000 * np.cos(2 * np.pi * 5 * t / 256)); snap[1, 1::2] = np.round(-20000 * np.sin(2 * np.pi * 5 * t / 256))     # -5 bins
+    p = A.grab_spectrum(snap)
+    x = snap[:, 0::2].astype(np.float64) + 1j * snap[:, 1::2].astype(np.float64)
+    ref = np.abs(np.fft.fft(x, axis=1)) ** 2
+    assert np.max(np.abs(p - ref) / ref.max(axis=1, keepdims=True)) < 2e-6
+    assert int(np.argmax(p[0])) == 5 and int(np.argmax(p[1])) == 251
+    z = A.grab_spectrum(np.zeros((1, 512), np.int16))
+    assert not z.any()
+
+
 def declared(prefixes=("sdr_preproc_", "sdr_iqgen_", "sdr_grabber_", "sdr_aux_")):
     src = open(os.path.join(ROOT, "include", "sdr_aux.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)

@@ -298,3 +298,29 @@ def test_grabber_matches_oracle(aux, chunks):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().astype(np.int32), want)
     g.close()
+
+
+def test_grabber_spectrum_matches_oracle(aux):
+    """Spectrum tap: power of the 256-point FFT of every channel's snapshot, bit for bit the oracle's
+    operation network; nothing before the first snapshot; the new-data flags are not consumed."""
+    import torch
+    from oracle import aux_lib as A
+    nch, nb = 70, 7
+    I, Q = S.pp_case(nch, nb, seed=5)
+    g = aux.GrabberBatch(nch)
+    assert g.spectrum() is None
+    g.process(_dev(I[:, :128]), _dev(Q[:, :128]), n_blocks=1)
+    assert g.spectrum([0, 3]) is None                       # one block: no pair has completed yet
+    g.process(_dev(I[:, 128:]), _dev(Q[:, 128:]), n_blocks=nb - 1)
+    snap, _ = A.grab_run(I, Q)
+    want = A.grab_spectrum(snap.astype(np.int16))
+    got = g.spectrum()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    pick = [69, 0, 17]
+    assert np.array_equal(g.spectrum(pick).view(np.uint32), want[pick].view(np.uint32))
+    dp = torch.empty((nch, 256), dtype=torch.float32, device="cuda:0")
+    assert g.spectrum_device(dp)
+    torch.cuda.synchronize()
+    assert np.array_equal(dp.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert g.newDataAvailable(0)                            # a spectrum is not a grab()
+    g.close()

@@ -19,7 +19,9 @@ ap.add_argument("--blocks", type=int, default=128)
 ap.add_argument("--start", default="")
 args = ap.parse_args()
 cfg_id = 2 if args.cls == "ssb" else 3
-nch = 4096 if args.cls != "envlean" else 16384   # envlean: enough groups for the two-per-SM plan (sdr_host.cpp, plan_bucket)
+nch = 4096 if args.cls not in ("envlean", "envmerged") else 16384   # enough groups for the plans that share an SM (sdr_host.cpp, plan_bucket)
+if args.cls == "envlean":
+    os.environ["SDR_NO_MERGE"] = "1"; os.environ["SDR_TILE_ENV"] = "16"; os.environ["SDR_CTAS_PER_SM"] = "2"
 os.environ["SDR_MAP_SEARCH"] = "1"               # the host re-plans at every call, so that it reads the placement variable again
 dev = torch.device("cuda:0")
 I16, Q16, calls = bench.synth_planes(dev, 0, nch, args.blocks * 128, 1234, cfg_id)
@@ -27,11 +29,13 @@ If, Qf = I16.float() / 32767.0, Q16.float() / 32767.0
 out = torch.empty((nch, args.blocks * 128), dtype=torch.float32, device=dev)
 b = api.SdrBatch(nch)
 b.configure(calls)
-var = {"ssb": "SDR_MAP_SSB", "env": "SDR_MAP_ENV", "envlean": "SDR_MAP_ENV_LEAN"}[args.cls]
-NW = 11 if args.cls == "envlean" else 14
+var = {"ssb": "SDR_MAP_SSB", "env": "SDR_MAP_ENV", "envlean": "SDR_MAP_ENV_LEAN", "envmerged": "SDR_MAP_ENV_MERGED"}[args.cls]
+NW = {"envlean": 11, "envmerged": 7}.get(args.cls, 14)
 stream = torch.cuda.current_stream()
 
 def pack(perm):
+    if args.cls == "envmerged":   # a string of program numbers, warp 0 first
+        return "".join(str(p) for p in perm)
     return "%X" % sum(s << (4 * w) for w, s in enumerate(perm))
 
 def measure(perm, reps=3):
@@ -47,7 +51,10 @@ def measure(perm, reps=3):
 def canon(perm):  # the four Hilbert warps (SSB stages 5..8) are interchangeable
     return tuple(5 if (args.cls == "ssb" and 5 <= s <= 8) else s for s in perm)
 
-start = [int(c, 16) for c in reversed(args.start)] if args.start else ([0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11] if args.cls == "envlean" else [5, 6, 7, 8, 2, 3, 11, 4, 9, 12, 10, 1, 0, 13])
+if args.cls == "envmerged":
+    start = [int(c) for c in args.start] if args.start else [1, 2, 0, 5, 4, 6, 3]
+else:
+    start = [int(c, 16) for c in reversed(args.start)] if args.start else ([0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11] if args.cls == "envlean" else [5, 6, 7, 8, 2, 3, 11, 4, 9, 12, 10, 1, 0, 13])
 for _ in range(3):
     measure(start)
 seen = {}
