@@ -38,7 +38,7 @@ class SdrError(RuntimeError):
 
 class Desc(C.Structure):
     _fields_ = [("n_channels", C.c_uint32), ("device", C.c_int32), ("max_blocks_per_call", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32)]
 
 
 class SetterCall(C.Structure):
@@ -113,12 +113,12 @@ def _fmt_of(dtype_name):
 class SdrBatch:
     """n_channels independent AudioSDR receivers on one GPU (one handle of include/sdr_batch.h)."""
 
-    def __init__(self, n_channels, device=0, max_blocks_per_call=0, _lib=None):
+    def __init__(self, n_channels, device=0, max_blocks_per_call=0, _lib=None, contract=False):
         self.L = _lib if _lib is not None else load_library()
         self.n_channels = int(n_channels)
         self.device = int(device)
         self.h = C.c_void_p()
-        d = Desc(self.n_channels, self.device, int(max_blocks_per_call), 0)
+        d = Desc(self.n_channels, self.device, int(max_blocks_per_call), 1 if contract else 0)  # flags: SDR_BATCH_CONTRACT
         self._check(self.L.sdr_batch_create(C.byref(self.h), C.byref(d)))
 
     # ---- plumbing

@@ -567,7 +567,7 @@ extern "C" uint64_t sdr_iqgen_launch_count(const sdr_iqgen_t *h) { return h ? h-
 /* Spectrum tap on the snapshots (the panadapter that consumes grab()): per channel the 256-point forward
  * complex FFT of the snapshot's (re, im) int16 pairs taken as floats, then the power re^2 + im^2 of every bin in natural bin
  * order.  One CTA = one channel, 128 threads = the 128 butterflies of a stage; the operation network is the radix-2
- * decimation-in-frequency one of the oracle (oracle/aux_fft128.h, aux_cfft_forward with n = 256), one rounding per operation. */
+ * decimation-in-frequency one the test suite's checker restates (aux_cfft256_forward), one rounding per operation. */
 __global__ void __launch_bounds__(128) grab_spectrum_kernel(const int16_t *snap, const uint32_t *channels, float *power) {
   __shared__ float2 buf[256];
   const uint32_t ch = channels ? channels[blockIdx.x] : blockIdx.x;

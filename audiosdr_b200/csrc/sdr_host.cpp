@@ -308,16 +308,16 @@ int env_int(const char *name, int dflt) { const char *e = getenv(name); return e
 int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
   /* Measured: the SSB class is bound by its four Hilbert warps per SM whatever the tile length, so it
    * stays on the 32-sample plan; an ENV group is bound by the latency of its one PLL warp, so ENV buckets without blanker
-   * and ALS run shorter tiles in a fraction of the shared memory -- 16-sample tiles, two groups per SM; SAM-only buckets
-   * 8-sample tiles with the light stages merged (7 warps), three groups per SM -- when there are enough groups to share. */
-  int T = 32, ctas = 1;
+   * and ALS run 16-sample tiles in a fraction of the shared memory -- two groups per SM; SAM-only buckets with the light
+   * stages merged (7 warps) three groups per SM -- when there are enough groups to share. */
+  int T = 32, ctas = 1, in_depth = 0;
   const bool lean = !(feat & (LF_NB | LF_ALS));
   if (cls == CLS_ENV && lean && b.count > (uint32_t)n_sm) {
-    if ((feat & LF_SAM) && b.count > 2u * (uint32_t)n_sm) { T = 8; ctas = 3; }
+    if ((feat & LF_SAM) && b.count > 2u * (uint32_t)n_sm) { T = 16; ctas = 3; in_depth = 1; } /* 76.7 KB: three fit an SM exactly */
     else { T = 16; ctas = 2; }
   }
   const int t_env = env_int(cls == CLS_SSB ? "SDR_TILE_SSB" : "SDR_TILE_ENV", 0);
-  if (t_env && lean) { T = t_env; ctas = T == 32 ? 1 : 2; }
+  if (t_env && lean) { T = t_env; ctas = T == 32 ? 1 : 2; in_depth = 0; }
   const int c_env = env_int("SDR_CTAS_PER_SM", 0);
   if (c_env > 0) ctas = c_env;
   if (env_int("SDR_NO_MERGE", 0)) feat &= ~(uint32_t)LF_SAM;
@@ -331,7 +331,7 @@ int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
     if (strlen(e) == 7) for (int w = 0; w < 7; w++) { mo[w] = (uint8_t)(e[w] - '0'); if (mo[w] < 7) seen |= 1u << mo[w]; }
     if (seen == 0x7Fu) merged_order = mo;
   }
-  int rc = lay_build_ex(&b.lay, cls, feat, T, budget > 232448 ? 232448 : budget, slack, env_int("SDR_IN_DEPTH", 0), merged_order);
+  int rc = lay_build_ex(&b.lay, cls, feat, T, budget > 232448 ? 232448 : budget, slack, env_int("SDR_IN_DEPTH", in_depth), merged_order);
   if (rc) rc = lay_build(&b.lay, cls, feat, 32, 232448, 0);
   if (rc) return rc;
   /* measured placements */
@@ -625,6 +625,7 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
   memset(&L, 0, sizeof L);
   L.in_i = I; L.in_q = Q; L.out = audio; L.in_pitch = in_pitch; L.out_pitch = out_pitch; L.in_fmt = in_fmt; L.out_fmt = out_fmt;
   L.blk0_mod3 = (uint32_t)(h->blocks_done % 3);
+  L.flags = h->desc.flags & SDR_BATCH_CONTRACT;
   L.cfg = h->d_cfg; L.state = h->d_state; L.ch_stride = h->ch_stride; L.agc_luts = h->d_luts; L.tabs = h->d_tabs;
   if (h->prof_on) {
     size_t need = (size_t)std::max<uint32_t>(h->n_groups, 1) * SDR_PROF_SLOTS * 8;
@@ -693,6 +694,7 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
    * reloads and saves the per-channel state, so chunks should not be tiny) */
   static const uint32_t want_chunks = []() { const char *e = getenv("SDR_HOST_CHUNKS"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 12); }();
   static const uint32_t min_chunk = []() { const char *e = getenv("SDR_HOST_MIN_CHUNK"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 16); }();
+  static const uint32_t ramp = []() { const char *e = getenv("SDR_HOST_RAMP"); int v = e ? atoi(e) : -1; return (uint32_t)(v >= 0 ? v : 8); }();
   uint32_t chunk = (n_blocks + want_chunks - 1) / want_chunks;
   if (chunk < min_chunk) chunk = min_chunk;
   if (chunk > n_blocks) chunk = n_blocks;
@@ -721,13 +723,27 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
   }
   /* work queued by an earlier process_device call on another stream must finish before the state is touched here */
   if (h->last_stream != h->s_comp && dev_sync(h->last_stream)) return SDR_ERR_CUDA;
+  /* Chunk lengths: `chunk` blocks in the middle of the call, ramping up from `ramp` blocks (doubling) at its start and down
+   * again at its end -- the first copy-in and the last kernel + copy-out are the only parts of the call nothing overlaps,
+   * so they are made short. */
+  std::vector<uint32_t> sizes;
+  {
+    std::vector<uint32_t> head;
+    uint32_t used = 0;
+    for (uint32_t r = ramp; r && r < chunk && used + 2 * r + chunk <= n_blocks; r *= 2) { head.push_back(r); used += 2 * r; }
+    uint32_t mid = n_blocks - used;
+    sizes = head;
+    const uint32_t n_mid = (mid + chunk - 1) / chunk;
+    for (uint32_t i = 0; i < n_mid; i++) { const uint32_t a = (uint32_t)((uint64_t)mid * i / n_mid), b = (uint32_t)((uint64_t)mid * (i + 1) / n_mid); sizes.push_back(b - a); }
+    for (size_t i = head.size(); i-- > 0;) sizes.push_back(head[i]);
+  }
   uint32_t done = 0, k = 0;
   int err = 0;
   /* on any failure the loop stops queueing and the streams are drained before returning: asynchronous copies into the
    * caller's buffers must not outlive the call */
 #define SDR_TRY(expr) if ((err = (expr)) != 0) break
   while (done < n_blocks) {
-    const uint32_t nb = std::min(chunk, n_blocks - done);
+    const uint32_t nb = sizes[k];
     const size_t w_in = (size_t)nb * SDR_BLOCK_SAMPLES * ies, w_out = (size_t)nb * SDR_BLOCK_SAMPLES * oes;
     const int b = (int)(k & 1);
     const char *srcI = (const char *)I + (size_t)done * SDR_BLOCK_SAMPLES * ies, *srcQ = (const char *)Q + (size_t)done * SDR_BLOCK_SAMPLES * ies;

@@ -15,8 +15,9 @@
 using namespace sdrk;
 
 extern "C" {
-int sdrk_setup_pipe_t32(const float *), sdrk_setup_pipe_t16(const float *), sdrk_setup_pipe_t8(const float *);
+int sdrk_setup_pipe_t32(const float *), sdrk_setup_pipe_t16(const float *), sdrk_setup_pipe_t8(const float *), sdrk_setup_pipe_t32c(const float *);
 int sdrk_launch_pipe_t32(const SdrLaunch *, void *), sdrk_launch_pipe_t16(const SdrLaunch *, void *), sdrk_launch_pipe_t8(const SdrLaunch *, void *);
+int sdrk_launch_pipe_t32c(const SdrLaunch *, void *);
 int sdrk_occupancy_t32(const SdrLaunch *), sdrk_occupancy_t16(const SdrLaunch *), sdrk_occupancy_t8(const SdrLaunch *);
 }
 
@@ -80,12 +81,13 @@ extern "C" int sdrk_setup_device(const float *hilbert64) {
   int e = sdrk_setup_pipe_t32(hilbert64);
   if (!e) e = sdrk_setup_pipe_t16(hilbert64);
   if (!e) e = sdrk_setup_pipe_t8(hilbert64);
+  if (!e) e = sdrk_setup_pipe_t32c(hilbert64);
   return e;
 }
 
 extern "C" int sdrk_launch_pipeline(const SdrLaunch *L, void *stream) {
   if (L->n_groups == 0) return 0;
-  if (L->lay.T == 32) return sdrk_launch_pipe_t32(L, stream);
+  if (L->lay.T == 32) return (L->flags & 1u) ? sdrk_launch_pipe_t32c(L, stream) : sdrk_launch_pipe_t32(L, stream);
   if (L->lay.T == 16) return sdrk_launch_pipe_t16(L, stream);
   if (L->lay.T == 8) return sdrk_launch_pipe_t8(L, stream);
   return 1;

@@ -307,8 +307,8 @@ static inline int lay_build_ex(SdrLay *L, int cls, uint32_t feat, int T, int bud
   if (merged) {
     static const uint8_t P[7][4] = {{ST_IN, ST_OUT, 0xFF, 0xFF}, {ST_IFI, 0xFF, 0xFF, 0xFF}, {ST_IFQ, 0xFF, 0xFF, 0xFF}, {ST_PLL, 0xFF, 0xFF, 0xFF},
                                     {ST_NCO2, ST_IMGI, ST_IMGQ, ST_MAG}, {ST_AUD, 0xFF, 0xFF, 0xFF}, {ST_AGC, 0xFF, 0xFF, 0xFF}};
-    /* placement: warp id % 4 = SM sub-partition; the PLL warp (the group's latency chain) gets the highest id of its own */
-    static const uint8_t order_default[7] = {1, 2, 0, 5, 4, 6, 3};
+    /* placement: warp id % 4 = SM sub-partition, the higher id has priority there */
+    static const uint8_t order_default[7] = {6, 4, 1, 3, 0, 5, 2}; /* measured: tools/map_search.py --cls envmerged */
     const uint8_t *order = merged_order ? merged_order : order_default;
     for (int w = 0; w < 7; w++) memcpy(L->prog[w], P[order[w]], 4);
     L->n_warps = 7;

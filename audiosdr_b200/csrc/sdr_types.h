@@ -140,6 +140,7 @@ typedef struct {
   const float *agc_luts; /* [n_luts][132] */
   const SdrTables *tabs;
   uint32_t n_groups;
+  uint32_t flags;        /* bit 0: the handle asked for the contracting build (sdr_batch_desc.flags & SDR_BATCH_CONTRACT) */
   uint32_t diag_skip;    /* diagnostics (profiling runs only): bit s set = stage s idles; results are then meaningless */
   unsigned long long *prof; /* optional [n_groups][SDR_PROF_SLOTS] (diagnostics twin): busy and waiting cycles per stage */
   SdrLay lay;

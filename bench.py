@@ -339,7 +339,7 @@ def fp32_roofline(peaks32, flop, samples_per_launch, launch_s):
 class Workload:
     """One BASELINE configuration on this rank's GPU: planes resident in HBM, a configured handle, timing and parity."""
 
-    def __init__(self, cfg_id, rank, world, local, dev, nblk=None, variant=()):
+    def __init__(self, cfg_id, rank, world, local, dev, nblk=None, variant=(), contract=False):
         import torch
         import audiosdr_b200 as A
         import signals as S
@@ -353,8 +353,9 @@ class Workload:
         self.I16, self.Q16, calls = synth_planes(dev, self.first, self.nch, self.ns, 0x5D120000 + cfg_id + rank, cfg_id)
         self.If = (self.I16.to(torch.float32) / 32767.0).contiguous(); self.Qf = (self.Q16.to(torch.float32) / 32767.0).contiguous()
         self.out = torch.empty((self.nch, self.ns), dtype=torch.float32, device=dev)
-        self.b = A.SdrBatch(self.nch, device=local)
+        self.b = A.SdrBatch(self.nch, device=local, contract=contract)
         self.b.configure(calls)
+        self.calls = calls
         if "nonb" in variant: self.b.disableNoiseBlanker(None)
         if "noagc" in variant: self.b.disableAGC(None)
         if "noaud" in variant: self.b.disableAudioFilter(None)
@@ -449,6 +450,7 @@ def main():
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--variant", default="", help="diagnostics only: comma list of nonb,noagc,noaud,als (changes the workload!)")
     ap.add_argument("--role-profile", action="store_true", help="per-stage busy fractions (adds clock reads; not for headline numbers)")
+    ap.add_argument("--contract", action="store_true", help="diagnostics only: the opt-in contracting build (not bit-exact) as the line's workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -469,11 +471,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = api.load_library()
     cfg_id = args.workload
-    diagnostic = cfg_id != CONFIG_ID or bool(args.variant) or args.role_profile
+    diagnostic = cfg_id != CONFIG_ID or bool(args.variant) or args.role_profile or args.contract
     if args.role_profile:
         os.environ["SDR_ROLE_PROFILE"] = "1"
     variant = tuple(v for v in args.variant.split(",") if v)
-    W = Workload(cfg_id, rank, world, local, dev, nblk=args.blocks_per_step if cfg_id == CONFIG_ID else None, variant=variant)
+    W = Workload(cfg_id, rank, world, local, dev, nblk=args.blocks_per_step if cfg_id == CONFIG_ID else None, variant=variant, contract=args.contract)
     nch, nblk, ns, b, I16, Q16 = W.nch, W.nblk, W.ns, W.b, W.I16, W.Q16
     parity, status = W.warm_up(max(args.warmup, 3))
 
@@ -497,6 +499,25 @@ def main():
         Ts = W.timed(n_sus, barrier)
         sustained = dict(value=Ts["value"], unit=UNIT, steps=n_sus, ms_per_step=Ts["ms_per_step"], seconds=Ts["ms_per_step"] * n_sus * 1e-3,
                          clocks=clk2.stop())
+
+    # ---- the opt-in contracting build on the same planes: what bit-exactness costs (a second number beside the exact one)
+    contracting = None
+    if not diagnostic and not args.only_headline:
+        try:
+            Wc = Workload.__new__(Workload)
+            Wc.__dict__.update({k: v for k, v in W.__dict__.items() if k != "b"})
+            Wc.b = A.SdrBatch(nch, device=local, contract=True)
+            Wc.b.configure(W.calls)
+            Wc.out = torch.empty_like(W.out)
+            for _ in range(3):
+                Wc.step()
+            torch.cuda.synchronize()
+            Tc = Wc.timed(args.steps, barrier)
+            contracting = dict(value=Tc["value"], unit=UNIT, ms_per_step=Tc["ms_per_step"], flag="SDR_BATCH_CONTRACT",
+                               note="fused multiply-adds + history-first sums in cascades / Hilbert / NCO; NOT bit-exact: see tests/test_gpu_long.py for the error profile")
+            del Wc.b, Wc.out
+        except Exception as e:
+            contracting = dict(error="%s: %s" % (type(e).__name__, e))
 
     # ---- end to end through the C ABI with HOST buffers (pinned int16 in, int16 out), copies inside the timed region
     hI = torch.empty((nch, ns), dtype=torch.int16).pin_memory(); hQ = torch.empty_like(hI).pin_memory()
@@ -588,7 +609,7 @@ def main():
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_fp32=fp32, cpu_baseline=cpu,
                     role_profile=role_profile, variant=args.variant or None,
                     diagnostic_workload=(None if cfg_id == CONFIG_ID else "BASELINE configs[%d], %d channels/GPU: NOT the headline metric" % (cfg_id - 1, nch)),
-                    parity=parity, status=status, host_affinity=affinity, sustained=sustained, workloads=workloads,
+                    parity=parity, status=status, host_affinity=affinity, sustained=sustained, contracting_build=contracting, workloads=workloads,
                     per_launch_ms=dict(mean=float(np.mean(per_launch_ms)), min=float(np.min(per_launch_ms)), max=float(np.max(per_launch_ms))))
         print(json.dumps(line), flush=True)
     if world > 1:

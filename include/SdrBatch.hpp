@@ -43,8 +43,8 @@ static const Channels all;
 class SdrBatch {
  public:
   /* AudioSDR::AudioSDR() -> init() for every channel (AudioSDR.h:77-79, AudioSDR.cpp:174-185) */
-  explicit SdrBatch(uint32_t n_channels, int device = 0, uint32_t max_blocks_per_call = 0) : h_(nullptr), n_(n_channels) {
-    sdr_batch_desc d = {n_channels, device, max_blocks_per_call, 0};
+  explicit SdrBatch(uint32_t n_channels, int device = 0, uint32_t max_blocks_per_call = 0, uint32_t flags = 0) : h_(nullptr), n_(n_channels) {
+    sdr_batch_desc d = {n_channels, device, max_blocks_per_call, flags};
     check(sdr_batch_create(&h_, &d), "sdr_batch_create");
   }
   ~SdrBatch() { sdr_batch_destroy(h_); }

@@ -38,6 +38,16 @@ def emu_lib():
 
 
 @pytest.fixture(scope="session")
+def emu_contract_lib():
+    """The same emulation built with -DSDR_CONTRACT: the arithmetic of the opt-in contracting build (tolerance tests)."""
+    import ctypes
+    from audiosdr_b200 import api
+    d = os.path.join(ROOT, "tests", "emu")
+    subprocess.run(["make", "-s", "-C", d, "libsdr_emu_contract.so"], check=True)
+    return api._bind(ctypes.CDLL(os.path.join(d, "libsdr_emu_contract.so")))
+
+
+@pytest.fixture(scope="session")
 def cuda_lib():
     """The real thing: audiosdr_b200/libsdr_batch.so on a CUDA device.  No fallback: absence is a failure."""
     import torch

@@ -13,10 +13,10 @@ N_BLOCK = 128
 STATUS_FIELDS = rc.STATUS_FIELDS
 
 
-def run_batch(lib, I, Q, events, chunks=(7, 1, 13), out_dtype=np.float32, device=None, return_batch=False):
+def run_batch(lib, I, Q, events, chunks=(7, 1, 13), out_dtype=np.float32, device=None, return_batch=False, contract=False):
     """I/Q: host arrays [C, S] (int16 or float32).  `device`: None -> process_host; a torch device -> process()."""
     nch, ns = I.shape
-    b = A.SdrBatch(nch, _lib=lib)
+    b = A.SdrBatch(nch, _lib=lib, contract=contract)
     ev = sorted(events, key=lambda e: e[1])
     nb_total = ns // N_BLOCK
     outs, pos, ei, k = [], 0, 0, 0

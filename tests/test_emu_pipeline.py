@@ -276,3 +276,30 @@ def test_emulated_short_tile_plans(oracle, emu_lib, monkeypatch, cfg, nch, nblk,
     a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(7, 1, 13), return_batch=True)
     assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
     assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+
+
+CONTRACT_TOL = 1e-4  # north_star: max abs error of full scale for the full chain
+
+
+@pytest.mark.parametrize("cfg,nch,nblk", [(1, 1, 200), (2, 24, 120), (3, 6, 120), (4, 35, 120), (5, 5, 120)])
+def test_emulated_contracting_build_error_profile(oracle, emu_contract_lib, cfg, nch, nblk):
+    """The opt-in contracting build (fused multiply-adds and history-first sums in the cascades, the Hilbert FIR and the NCO
+    product) is not bit-exact.  Up to the AGC its output stays far inside north_star's 1e-4 of full scale (checked with the
+    AGC off: a few 1e-5 at most).  Behind the AGC a 1-ulp difference of the level can move the index into the reference's 129-entry
+    gain table (C:419, C:483-494) by one step, which -- on the table's steep first segment -- changes the gain of that one
+    sample by up to ~0.6 %: isolated samples beyond 1e-4, which no non-bit-exact build can avoid.  That is
+    why the exact build is the default and the product's parity claim; this test pins the size and rarity of the effect."""
+    I, Q, ev = S.make(cfg, list(range(nch)), nblk)
+    o = oracle.run(I, Q, ev, threads=4)
+    a = harness.run_batch(emu_contract_lib, I, Q, ev, chunks=(7, 1, 13))
+    err = np.abs(a.astype(np.float64) - o["audio"])
+    assert float(np.mean(err > CONTRACT_TOL)) < 1e-4 and float(err.max()) < 5e-3, "max %g, share above tolerance %g" % (err.max(), np.mean(err > CONTRACT_TOL))
+    assert float(np.sqrt(np.mean(err ** 2))) < 2e-6
+    assert not harness.bits_equal(a, o["audio"])  # it really is the other arithmetic
+    ev_noagc = ev + [(c, 0, "disableAGC") for c in range(nch)]
+    o2 = oracle.run(I, Q, ev_noagc, threads=4)
+    a2 = harness.run_batch(emu_contract_lib, I, Q, ev_noagc, chunks=(7, 1, 13))
+    fin = np.isfinite(o2["audio"]).all(axis=1) & np.isfinite(a2).all(axis=1)  # (config 4: without AGC the adaptive ALS runs away, in the reference too)
+    if fin.any():
+        scale = max(1.0, float(np.max(np.abs(o2["audio"][fin]))))
+        assert float(np.max(np.abs(a2[fin].astype(np.float64) - o2["audio"][fin]))) <= CONTRACT_TOL * scale
