@@ -608,6 +608,7 @@ struct sdr_grabber {
 extern "C" int sdr_grabber_create(sdr_grabber_t **out, uint32_t n_channels, int device) {
   if (!out || n_channels == 0) return fail(SDR_AUX_EINVAL, "sdr_grabber_create: bad arguments");
   CK(cudaSetDevice(device));
+  if (int rc = upload_tables()) return rc; /* the spectrum tap's twiddles */
   sdr_grabber *h = new sdr_grabber();
   h->n = n_channels; h->device = device; h->fresh.assign(n_channels, 0);
   if (cudaMalloc(&h->half[0], 512 * (size_t)n_channels) != cudaSuccess || cudaMalloc(&h->half[1], 512 * (size_t)n_channels) != cudaSuccess ||

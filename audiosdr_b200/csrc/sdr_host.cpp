@@ -694,7 +694,7 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
    * reloads and saves the per-channel state, so chunks should not be tiny) */
   static const uint32_t want_chunks = []() { const char *e = getenv("SDR_HOST_CHUNKS"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 12); }();
   static const uint32_t min_chunk = []() { const char *e = getenv("SDR_HOST_MIN_CHUNK"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 16); }();
-  static const uint32_t ramp = []() { const char *e = getenv("SDR_HOST_RAMP"); int v = e ? atoi(e) : -1; return (uint32_t)(v >= 0 ? v : 8); }();
+  static const uint32_t ramp = []() { const char *e = getenv("SDR_HOST_RAMP"); int v = e ? atoi(e) : -1; return (uint32_t)(v >= 0 ? v : 0); }();
   uint32_t chunk = (n_blocks + want_chunks - 1) / want_chunks;
   if (chunk < min_chunk) chunk = min_chunk;
   if (chunk > n_blocks) chunk = n_blocks;
@@ -723,9 +723,9 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
   }
   /* work queued by an earlier process_device call on another stream must finish before the state is touched here */
   if (h->last_stream != h->s_comp && dev_sync(h->last_stream)) return SDR_ERR_CUDA;
-  /* Chunk lengths: `chunk` blocks in the middle of the call, ramping up from `ramp` blocks (doubling) at its start and down
-   * again at its end -- the first copy-in and the last kernel + copy-out are the only parts of the call nothing overlaps,
-   * so they are made short. */
+  /* Chunk lengths: `chunk` blocks each.  SDR_HOST_RAMP=r (experiment, default off) ramps up from r blocks (doubling) at the
+   * start of the call and down again at its end: the first copy-in and the last kernel + copy-out are the only parts of the
+   * call nothing overlaps.  Measured: no gain beyond the run-to-run spread of the host link (profiles/README.md). */
   std::vector<uint32_t> sizes;
   {
     std::vector<uint32_t> head;
