@@ -129,14 +129,16 @@ __device__ __forceinline__ void run_envelope_path(const Ctx &x, int lane) {
   lockstep_loop(x, [&](uint32_t s) {
     uint32_t t;
     if (!tile_at(x, ST_NCO2, s, t)) return;
-    n2.step(x, lane, t);
-    __syncwarp();
     if (__any_sync(0xffffffffu, n2.cid >= 0 && env_flag(x, lane, t) != 0)) {
+      n2.step(x, lane, t);
+      __syncwarp();
 #pragma unroll 1
       for (int rail = 0; rail < 2; rail++) { RoleBiquad r; r.load(x, lane, 2, rail); r.step(x, lane, t); r.save(x); }
+      __syncwarp();
+      mg.step(x, lane, t);
+    } else {
+      mg.pass_locked(x, lane, t);
     }
-    __syncwarp();
-    mg.step(x, lane, t);
     x.k.advance(x);
   });
   n2.save(x); mg.save(x);
