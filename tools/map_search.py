@@ -17,8 +17,10 @@ ap.add_argument("--cls", default="ssb")
 ap.add_argument("--seconds", type=float, default=150.0)
 ap.add_argument("--blocks", type=int, default=128)
 ap.add_argument("--start", default="")
+ap.add_argument("--als", action="store_true", help="enable the ALS filter on every channel (the placement of buckets with ALS)")
+ap.add_argument("--config", type=int, default=0, help="BASELINE config to take signals and setters from (default: 2 for ssb, 3 for env)")
 args = ap.parse_args()
-cfg_id = 2 if args.cls == "ssb" else 3
+cfg_id = args.config or (2 if args.cls == "ssb" else 3)
 nch = 4096 if args.cls not in ("envlean", "envmerged") else 16384   # enough groups for the plans that share an SM (sdr_host.cpp, plan_bucket)
 if args.cls == "envlean":
     os.environ["SDR_NO_MERGE"] = "1"; os.environ["SDR_TILE_ENV"] = "16"; os.environ["SDR_CTAS_PER_SM"] = "2"
@@ -29,6 +31,8 @@ If, Qf = I16.float() / 32767.0, Q16.float() / 32767.0
 out = torch.empty((nch, args.blocks * 128), dtype=torch.float32, device=dev)
 b = api.SdrBatch(nch)
 b.configure(calls)
+if args.als:
+    b.enableALSfilter(None)
 var = {"ssb": "SDR_MAP_SSB", "env": "SDR_MAP_ENV", "envlean": "SDR_MAP_ENV_LEAN", "envmerged": "SDR_MAP_ENV_MERGED"}[args.cls]
 NW = {"envlean": 11, "envmerged": 7}.get(args.cls, 14)
 stream = torch.cuda.current_stream()
