@@ -187,6 +187,7 @@ static inline int lay_check(const SdrLay *L) {
   const int lim = SDR_BAR_W - 2;
   if (L->nr > lim || L->na > lim || L->nc > lim || L->nz > lim || L->nz2 > lim || L->ni > lim || L->tpb + 2 > lim) return 3;
   if (L->smem_bytes > 232448) return 4;
+  if ((L->o_ins | L->o_outs | (L->ins_row * 4) | L->o_lut) & 15) return 5; /* bulk copies move 16-byte aligned rows */
   return 0;
 }
 

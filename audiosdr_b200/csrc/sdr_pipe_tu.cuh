@@ -278,6 +278,10 @@ __device__ __forceinline__ void pipeline_cta(const SdrLaunch &L, unsigned char *
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 #endif
+#ifndef SDR_NO_BULK_IO
+  if (threadIdx.x < 4) bulk_bar_init(smem + x.o_lut() + SDR_INBAR_OFF + 8 * threadIdx.x, SDR_LANES); /* input landing buffers: every lane of stage IN arrives */
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
   __syncthreads(); /* stage IN requests its first tile from load(), which needs the channel ids */
   for (int i = threadIdx.x; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i += nthr) { /* the group's AGC tables */
     const int id = x.G->lut_ids[i / SDR_AGC_LUT_STRIDE];

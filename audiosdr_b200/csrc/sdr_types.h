@@ -150,6 +150,8 @@ typedef struct {
  * scheduler) for the launches that run all 14 stages; SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */
 #define SDR_MAP_SSB_DEFAULT 0x3BADC548961720ull
 #define SDR_MAP_ENV_DEFAULT 0xA0D459B1328C67ull
+#define SDR_MAP_SSB_ALS_DEFAULT 0x4630127BC98DA5ull /* SSB buckets with the ALS filter: its stage (ALS + output) is by far the slowest and wants a
+                                                        sub-partition where it wins the scheduler (tools/map_search.py --cls ssb --als) */
 #define SDR_MAP_ENV_LEAN_DEFAULT 0x52980364BA7ull /* the 11-warp ENV plan on 16-sample tiles, two groups per SM (tools/map_search.py --cls envlean) */
 
 #define SDR_PROF_SLOTS 64 /* [0..15] busy cycles per stage, [16..31] cycles waiting for other stages, [32] CTA cycles, [33] prologue (diagnostics twin only) */
