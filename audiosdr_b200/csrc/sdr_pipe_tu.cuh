@@ -278,7 +278,7 @@ __device__ __forceinline__ void pipeline_cta(const SdrLaunch &L, unsigned char *
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 #endif
-#ifndef SDR_NO_BULK_IO
+#ifdef SDR_BULK_IO
   if (threadIdx.x < 4) bulk_bar_init(smem + x.o_lut() + SDR_INBAR_OFF + 8 * threadIdx.x, SDR_LANES); /* input landing buffers: every lane of stage IN arrives */
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
