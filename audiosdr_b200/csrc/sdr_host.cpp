@@ -135,7 +135,12 @@ void build_agc_lut(float thr, float slope, float knee, float *lut) {
 }  // namespace
 
 /* the groups of one pipeline class with one set of optional stages: one kernel launch with its own shared-memory plan */
-struct Bucket { SdrLay lay; uint32_t first, count; };
+struct Bucket {
+  SdrLay lay; uint32_t first, count;
+  /* a bucket with the ALS filter and more groups than SMs runs as two launches (sdr_lay.h, lay_build_als): the chain up to
+   * the AGC on the plan the bucket would have without ALS, then the ALS + output post-pass, four groups to an SM */
+  bool split; SdrLay lay_main, lay_als;
+};
 
 struct sdr_batch {
   sdr_batch_desc desc;
@@ -157,6 +162,7 @@ struct sdr_batch {
   void *d_in_i[2], *d_in_q[2], *d_out[2]; size_t stage_in_bytes, stage_out_bytes;
   void *s_h2d, *s_comp, *s_d2h; void *ev_h2d[2], *ev_comp[2], *ev_d2h[2];
   uint32_t n_groups;
+  float *d_raw[9]; size_t raw_cap[9]; /* scratch planes of split ALS buckets (by bucket index), grown on demand */
   unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
   std::vector<uint64_t> prof_busy, prof_total, prof_groups, prof_extra, prof_load, prof_crit, prof_bar; /* folded per class */
   uint64_t blocks_done, launches;
@@ -344,6 +350,14 @@ int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
     if (const char *e = getenv("SDR_MAP_ENV_LEAN")) m = strtoull(e, nullptr, 16);
     lay_place(&b.lay, m);
   } else if (const char *e = getenv("SDR_MAP_SSB_LEAN")) lay_place(&b.lay, strtoull(e, nullptr, 16));
+  /* ALS buckets: one launch while every group has an SM to itself (the ALS warp then runs beside the chain at no cost in
+   * waves); two launches beyond that.  SDR_ALS_SPLIT=0 / 1 forces one form (tests, A/B runs). */
+  b.split = false;
+  const int sp = env_int("SDR_ALS_SPLIT", -1);
+  if ((feat & LF_ALS) && sp != 0 && (b.count > (uint32_t)n_sm || sp == 1)) {
+    Bucket m; m.first = b.first; m.count = b.count;
+    if (plan_bucket(m, cls, feat & ~(uint32_t)LF_ALS, n_sm) == 0 && lay_build_als(&b.lay_als) == 0) { b.lay_main = m.lay; b.split = true; }
+  }
   return 0;
 }
 
@@ -523,6 +537,7 @@ void sdr_batch_destroy(sdr_batch_t *h) {
   for (int k = 0; k < 8; k++) { if (h->s_aux[k]) dev_sync(h->s_aux[k]); dev_stream_destroy(h->s_aux[k]); dev_event_destroy(h->ev_join[k]); }
   dev_event_destroy(h->ev_fork);
   dev_free(h->d_prof);
+  for (int k = 0; k < 9; k++) dev_free(h->d_raw[k]);
   delete h;
 }
 
@@ -542,6 +557,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->s_h2d = h->s_comp = h->s_d2h = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0;
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
+  for (int k = 0; k < 9; k++) { h->d_raw[k] = nullptr; h->raw_cap[k] = 0; }
   h->ev_fork = nullptr; for (int k = 0; k < 8; k++) { h->s_aux[k] = nullptr; h->ev_join[k] = nullptr; }
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
   h->prof_busy.assign(2 * SDR_STAGES, 0); h->prof_crit.assign(32, 0); h->prof_bar.assign(2 * SDR_STAGES, 0); h->prof_extra.assign(16, 0); h->prof_load.assign(2 * (SDR_STAGES + 1), 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
@@ -656,18 +672,49 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
     L.prof = h->prof_on ? h->d_prof + (size_t)b.first * SDR_PROF_SLOTS : nullptr;
     if (getenv("SDR_DEBUG_PLAN")) {
       static int shown = 0;
-      if (shown++ < 8)
-#ifndef SDR_EMU
-        fprintf(stderr, "[sdr] launch: class %d feat %u T %d warps %d smem %d B groups %u -> %d CTA(s)/SM; rings nr %d na %d nc %d ni %d hq %d nz %d nz2 %d, input depth %d\n",
-                b.lay.cls, b.lay.feat, b.lay.T, b.lay.n_warps, b.lay.smem_bytes, b.count, sdrk_occupancy(&L), b.lay.nr, b.lay.na, b.lay.nc, b.lay.ni,
-                b.lay.hq_tiles, b.lay.nz, b.lay.nz2, b.lay.in_depth);
-#else
-        fprintf(stderr, "[sdr] launch: class %d feat %u T %d warps %d smem %d B groups %u\n", b.lay.cls, b.lay.feat, b.lay.T, b.lay.n_warps, b.lay.smem_bytes, b.count);
-#endif
+      const bool two = b.split && !h->prof_on;
+      auto show = [&](const SdrLay &y, const char *what) {
+        SdrLaunch P = L; P.lay = y;
+        fprintf(stderr, "[sdr] %s: class %d feat %u T %d warps %d smem %d B groups %u -> %d CTA(s)/SM; rings nr %d na %d nc %d ni %d hq %d nz %d nz2 %d, input depth %d\n",
+                what, y.cls, y.feat, y.T, y.n_warps, y.smem_bytes, b.count, sdrk_occupancy(&P), y.nr, y.na, y.nc, y.ni, y.hq_tiles, y.nz, y.nz2, y.in_depth);
+      };
+      if (shown++ < 8) {
+        if (two) { show(b.lay_main, "launch (chain of a split ALS bucket)"); show(b.lay_als, "launch (ALS post-pass)"); }
+        else show(b.lay, "launch");
+      }
     }
-    int e = sdrk_launch_pipeline(&L, s);
-    if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
-    h->launches++;
+    if (b.split && !h->prof_on && k < 9) {
+      /* two launches per slice of the call; the scratch plane holds one slice (SDR_ALS_SCRATCH_MB bounds it, 4 GB by default:
+       * a slice is then 2 048 blocks of 16 384 channels, long enough that the state reload per slice does not show) */
+      const size_t per_block = (size_t)b.count * SDR_BLOCK_SAMPLES * SDR_LANES * sizeof(float);
+      const size_t cap = (size_t)std::max(env_int("SDR_ALS_SCRATCH_MB", 4096), 1) << 20;
+      const uint32_t slice = (uint32_t)std::min<size_t>(n_blocks, std::max<size_t>(cap / per_block, 16));
+      if (h->raw_cap[k] < slice * per_block) {
+        if (h->d_raw[k]) { if (dev_sync(h->last_stream)) return SDR_ERR_CUDA; dev_free(h->d_raw[k]); h->d_raw[k] = nullptr; h->raw_cap[k] = 0; }
+        if (dev_alloc((void **)&h->d_raw[k], slice * per_block)) return SDR_ERR_NOMEM;
+        h->raw_cap[k] = slice * per_block;
+      }
+      const size_t ies = in_fmt == SDR_FMT_F32 ? 4 : 2, oes = out_fmt == SDR_FMT_F32 ? 4 : 2;
+      for (uint32_t b0 = 0; b0 < n_blocks; b0 += slice) {
+        const uint32_t nb = std::min(slice, n_blocks - b0);
+        SdrLaunch M = L;
+        M.in_i = (const char *)I + (size_t)b0 * SDR_BLOCK_SAMPLES * ies; M.in_q = (const char *)Q + (size_t)b0 * SDR_BLOCK_SAMPLES * ies;
+        M.out = (char *)audio + (size_t)b0 * SDR_BLOCK_SAMPLES * oes;
+        M.blk0_mod3 = (uint32_t)((h->blocks_done + b0) % 3);
+        M.raw = h->d_raw[k];
+        SdrLaunch A = M;
+        M.lay = b.lay_main; M.n_tiles = nb * (uint32_t)b.lay_main.tpb; M.flags |= SDRL_RAW_OUT;
+        A.lay = b.lay_als; A.n_tiles = nb * (uint32_t)b.lay_als.tpb;
+        int e = sdrk_launch_pipeline(&M, s);
+        if (!e) e = sdrk_launch_als_pass(&A, s);
+        if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
+        h->launches += 2;
+      }
+    } else {
+      int e = sdrk_launch_pipeline(&L, s);
+      if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");
+      h->launches++;
+    }
     if (k > 0 && (dev_event_record(h->ev_join[k - 1], s) || dev_stream_wait(stream, h->ev_join[k - 1]))) return SDR_ERR_CUDA;
   }
   h->blocks_done += n_blocks;

@@ -19,6 +19,7 @@ int sdrk_setup_pipe_t32(const float *), sdrk_setup_pipe_t16(const float *), sdrk
 int sdrk_launch_pipe_t32(const SdrLaunch *, void *), sdrk_launch_pipe_t16(const SdrLaunch *, void *), sdrk_launch_pipe_t8(const SdrLaunch *, void *);
 int sdrk_launch_pipe_t32c(const SdrLaunch *, void *);
 int sdrk_occupancy_t32(const SdrLaunch *), sdrk_occupancy_t16(const SdrLaunch *), sdrk_occupancy_t8(const SdrLaunch *);
+int sdrk_setup_als_pass(void), sdrk_occupancy_als_pass(const SdrLaunch *); /* sdr_als_pass.cu */
 }
 
 /* Zero (or re-seed) state words of listed channels: the side effects of the reference setters that
@@ -82,6 +83,7 @@ extern "C" int sdrk_setup_device(const float *hilbert64) {
   if (!e) e = sdrk_setup_pipe_t16(hilbert64);
   if (!e) e = sdrk_setup_pipe_t8(hilbert64);
   if (!e) e = sdrk_setup_pipe_t32c(hilbert64);
+  if (!e) e = sdrk_setup_als_pass();
   return e;
 }
 
@@ -94,6 +96,7 @@ extern "C" int sdrk_launch_pipeline(const SdrLaunch *L, void *stream) {
 }
 
 extern "C" int sdrk_occupancy(const SdrLaunch *L) {
+  if (L->lay.cls == CLS_ALS) return sdrk_occupancy_als_pass(L);
   return L->lay.T == 32 ? sdrk_occupancy_t32(L) : (L->lay.T == 16 ? sdrk_occupancy_t16(L) : sdrk_occupancy_t8(L));
 }
 

@@ -18,6 +18,7 @@ extern "C" {
 #endif
 int sdrk_setup_device(const float *hilbert64);
 int sdrk_launch_pipeline(const SdrLaunch *L, void *stream);
+int sdrk_launch_als_pass(const SdrLaunch *L, void *stream); /* second launch of a split ALS bucket (L->lay from lay_build_als, L->raw) */
 int sdrk_occupancy(const SdrLaunch *L); /* resident CTAs per SM granted to this launch configuration (diagnostics) */
 int sdrk_launch_reset(float *state, unsigned long long ch_stride, const uint32_t *chan, const uint32_t *mask, uint32_t n, void *stream);
 int sdrk_launch_fill_word(float *state, unsigned long long ch_stride, uint32_t w, float v, uint32_t n_ch, void *stream);

@@ -325,6 +325,35 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
   return lay_build_ex(L, cls, feat, T, budget, max_slack, 0, (const uint8_t *)0);
 }
 
+/* The ALS + output post-pass (SdrLay::cls == CLS_ALS).  The LMS line enhancer (C:324-352) is the chain's last stage and by far
+ * its slowest (one warp sweeps 55 taps for every 4 samples, each sweep waiting for the error of the sweep before), and a
+ * group that carries it fills an SM's shared memory, so a bucket with more groups than SMs queues in waves whose length the
+ * ALS warp sets.  Such a bucket runs in two launches instead: the chain up to the AGC -- the bucket's plan without ALS, its
+ * output stage writing the AGC output tiles as they are to a scratch plane (SdrLaunch::flags & SDRL_RAW_OUT) -- and this
+ * plan: ONE warp per group that fetches the scratch tiles one tile ahead (asynchronous copies straight into the ALS input
+ * ring: the scratch plane has the ring's [sample][lane] layout) and runs the chain's ALS + output stage unchanged.  49.5 KB
+ * per group: four groups share an SM, each on a scheduler of its own, and 592 groups run at once.
+ * Ring: the sweep for a tile reaches back M + delay <= 129 samples and loads (without using) up to 9 more; with 7 slots the
+ * slot being filled one tile ahead is never one a sweep touches.  A single warp in program order: no hand-over rules. */
+static inline int lay_build_als(SdrLay *L) {
+  memset(L, 0, sizeof *L);
+  const int T = 32, tile_b = T * SDR_LANES * 4;
+  L->cls = CLS_ALS; L->feat = LF_ALS; L->T = T; L->tpb = 4; L->tpb_sh = 2; L->tile_f = T * SDR_LANES;
+  L->active[ST_IN] = L->active[ST_OUT] = 1;
+  for (int s = 0; s < 16; s++) { L->bar_of[s] = (uint8_t)s; L->bar_count[s] = 1; }
+  L->nr = L->na = L->ni = L->nz = L->nz2 = L->hq_tiles = 1; L->nc = L->tpb + 3; L->ins_row = T + 4; L->in_depth = 1;
+  int o = 0;
+  L->o_cid = o; o += 128;
+  L->o_alsc = o; o += 128 * SDR_LANES * 4;
+  L->o_outs = o; o += SDR_LANES * L->ins_row * 4;
+  L->o_c = o; o += L->nc * tile_b;
+  L->smem_bytes = o;
+  memset(L->prog, 0xFF, sizeof L->prog);
+  L->n_warps = 1; L->prog[0][0] = ST_IN; L->prog[0][1] = ST_OUT; L->stage_of_warp[0] = ST_IN;
+  for (int s = 0; s < SDR_STAGES; s++) for (int i = 0; i < SDR_MAX_DEPS; i++) { L->deps[s][i].stage = -1; L->deps[s][i].kind = 0; L->deps[s][i].k = 0; }
+  return 0;
+}
+
 /* placement: `map` = stage id of physical warp w in bits 4w..4w+3 (as many nibbles as the launch has warps); ignored unless it
  * names every active stage exactly once */
 static inline int lay_place(SdrLay *L, unsigned long long map) {

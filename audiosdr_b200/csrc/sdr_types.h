@@ -79,7 +79,8 @@ typedef struct {
 } SdrChanCfg;
 
 /* ---- pipeline classes ---- */
-enum { CLS_SSB = 0 /* LSB USB CW_LSB CW_USB WSPR: NCO + Hilbert */, CLS_ENV = 1 /* AM SAM: PLL + envelope */ };
+enum { CLS_SSB = 0 /* LSB USB CW_LSB CW_USB WSPR: NCO + Hilbert */, CLS_ENV = 1 /* AM SAM: PLL + envelope */,
+       CLS_ALS = 2 /* not a channel class: the plan of the ALS + output post-pass of a large bucket (sdr_lay.h, lay_build_als) */ };
 
 #define SDR_LUT_SLOTS 4
 typedef struct {
@@ -140,11 +141,17 @@ typedef struct {
   const float *agc_luts; /* [n_luts][132] */
   const SdrTables *tabs;
   uint32_t n_groups;
-  uint32_t flags;        /* bit 0: the handle asked for the contracting build (sdr_batch_desc.flags & SDR_BATCH_CONTRACT) */
+  uint32_t flags;        /* SDRL_CONTRACT: the handle asked for the contracting build (sdr_batch_desc.flags & SDR_BATCH_CONTRACT);
+                            SDRL_RAW_OUT: first launch of a split ALS bucket -- the output stage writes the AGC output as it is (float32, no
+                            ALS, gain, mute or truncation) to the scratch plane the ALS post-pass reads */
+  float *raw;            /* split ALS bucket: scratch plane [group of the launch][sample of the call][lane] (float32), written by the
+                            SDRL_RAW_OUT launch, read by the ALS post-pass (sdr_als_pass.cu) */
   uint32_t diag_skip;    /* diagnostics (profiling runs only): bit s set = stage s idles; results are then meaningless */
   unsigned long long *prof; /* optional [n_groups][SDR_PROF_SLOTS] (diagnostics twin): busy and waiting cycles per stage */
   SdrLay lay;
 } SdrLaunch;
+
+enum { SDRL_CONTRACT = 1u, SDRL_RAW_OUT = 2u };
 
 /* default placement of the stages on the warps of a CTA (warp id % 4 = SM sub-partition, higher id = preferred by the
  * scheduler) for the launches that run all 14 stages; SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */

@@ -104,10 +104,10 @@ static bool runnable(const SdrLay &Y, const std::vector<long long> &done, int s,
   return true;
 }
 
-int run_group(const SdrLaunch &L, const SdrGroup &G) {
+int run_group(const SdrLaunch &L, const SdrGroup &G, int gidx) {
   const SdrLay &Y = L.lay;
   std::vector<unsigned char> smem((size_t)Y.smem_bytes, 0xFF);
-  Ctx x; x.L = &L; x.Y = &L.lay; x.G = &G; x.smem = smem.data(); x.gidx = 0; x.t0 = 0; x.prof = false;
+  Ctx x; x.L = &L; x.Y = &L.lay; x.G = &G; x.smem = smem.data(); x.gidx = gidx; x.t0 = 0; x.prof = false;
   for (int i = 0; i < 257; i++) x.f(Y.o_sine)[i] = L.tabs->sine[i];
   for (int i = 0; i < 32; i++) reinterpret_cast<int *>(smem.data() + Y.o_cid)[i] = G.cid[i];
   for (int i = 0; i < SDR_LUT_SLOTS * SDR_AGC_LUT_STRIDE; i++) {
@@ -164,6 +164,29 @@ int run_group(const SdrLaunch &L, const SdrGroup &G) {
   return 0;
 }
 
+/* the ALS + output post-pass (sdr_als_pass.cu): one warp in program order, lane by lane between the kernel's warp barriers */
+int run_als_group(const SdrLaunch &L, const SdrGroup &G, int gidx) {
+  const SdrLay &Y = L.lay;
+  std::vector<unsigned char> smem((size_t)Y.smem_bytes, 0xFF);
+  Ctx x; x.L = &L; x.Y = &L.lay; x.G = &G; x.smem = smem.data(); x.gidx = gidx; x.t0 = 0; x.prof = false;
+  for (int i = 0; i < 32; i++) reinterpret_cast<int *>(smem.data() + Y.o_cid)[i] = G.cid[i];
+  emu_async_owner() = ST_OUT;
+  std::vector<RoleOut> out(32);
+  x.k.reset();
+  for (int lane = 0; lane < 32; lane++) out[lane].load(x, lane);
+  const uint32_t n = L.n_tiles;
+  for (int lane = 0; lane < 32; lane++) RoleAlsIn::request(x, lane, 0, 0);
+  for (uint32_t t = 0; t < n; t++) {
+    cp_async_wait_pending(0);
+    if (t + 1 < n) for (int lane = 0; lane < 32; lane++) RoleAlsIn::request(x, lane, t + 1, Slots::next(x.k.c, Y.nc));
+    for (int lane = 0; lane < 32; lane++) out[lane].step_a(x, lane, t);
+    for (int lane = 0; lane < 32; lane++) out[lane].step_b(x, lane, t);
+    x.k.advance(x);
+  }
+  for (int lane = 0; lane < 32; lane++) out[lane].save(x, lane);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -172,7 +195,13 @@ int sdrk_setup_device(const float *hilbert64) { memcpy(g_hilbert, hilbert64, siz
 
 int sdrk_launch_pipeline(const SdrLaunch *L, void *) {
   if (lay_check(&L->lay)) return 100 + lay_check(&L->lay);
-  for (uint32_t g = 0; g < L->n_groups; g++) { int e = run_group(*L, L->groups[g]); if (e) return e; }
+  for (uint32_t g = 0; g < L->n_groups; g++) { int e = run_group(*L, L->groups[g], (int)g); if (e) return e; }
+  return 0;
+}
+
+int sdrk_launch_als_pass(const SdrLaunch *L, void *) {
+  if (L->lay.cls != CLS_ALS || !L->raw) return 99;
+  for (uint32_t g = 0; g < L->n_groups; g++) { int e = run_als_group(*L, L->groups[g], (int)g); if (e) return e; }
   return 0;
 }
 

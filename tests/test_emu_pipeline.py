@@ -278,6 +278,58 @@ def test_emulated_short_tile_plans(oracle, emu_lib, monkeypatch, cfg, nch, nblk,
     assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
 
 
+@pytest.mark.parametrize("sched", ["lockstep", "lockstep-reversed", "consumers", "random:4/late"])
+@pytest.mark.parametrize("case", ["config4", "edge", "sliced", "sam"])
+def test_emulated_split_als_bucket(oracle, emu_lib, monkeypatch, case, sched):
+    """A bucket with the ALS filter and more groups than SMs runs as two launches -- the chain up to the AGC into a scratch
+    plane, then the ALS + output post-pass (sdr_lay.h, lay_build_als): same bits, whatever plan the chain runs on, also when
+    the scratch plane only holds a slice of the call."""
+    set_schedule(monkeypatch, sched)
+    monkeypatch.setenv("SDR_ALS_SPLIT", "1")
+    chunks = (7, 1, 13)
+    if case == "config4":
+        I, Q, ev = S.make(4, list(range(70)), 24)
+    elif case == "edge":
+        nch = 2 * len(ALS_EDGE_PARAMS)
+        I, Q, ev = S.make(4, list(range(nch)), 14)
+        ev = [e for e in ev if not e[2].startswith("setALSfilterParams")] + als_edge_events(nch)
+        chunks = (3, 1, 6, 4)
+    elif case == "sliced":  # 3 groups: 48 KB of scratch per block, 1 MB holds 21 blocks -> the 40-block call runs as two slices
+        monkeypatch.setenv("SDR_ALS_SCRATCH_MB", "1")
+        I, Q, ev = S.make(4, list(range(20)), 40)
+        chunks = (40,)
+    else:  # SAM channels with ALS and nothing else: the chain runs on the merged 7-warp plan with 16-sample tiles
+        monkeypatch.setenv("SDR_TILE_ENV", "16"); monkeypatch.setenv("SDR_CTAS_PER_SM", "3"); monkeypatch.setenv("SDR_IN_DEPTH", "1")
+        I, Q, ev = S.make(3, list(range(6)), 30)
+        ev += [(c, 0, "enableALSfilter") for c in range(6)] + [(c, 0, "setALSfilterNotch" if c % 2 else "setALSfilterPeak") for c in range(6)]
+    o = oracle.run(I, Q, ev, threads=4)
+    a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=chunks, return_batch=True)
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+    p = harness.run_batch(emu_lib, I, Q, ev, chunks=(3, 11), out_dtype=np.int16)
+    assert np.array_equal(p, o["pcm"])
+
+
+def test_emulated_als_forms_alternate_between_calls(oracle, emu_lib, monkeypatch):
+    """The one-launch and the two-launch form of an ALS bucket keep the same state words: a handle may change form from call
+    to call (the plan is made again whenever the grouping changes)."""
+    import audiosdr_b200 as A
+    I, Q, ev = S.make(4, list(range(40)), 20)
+    want = oracle.run(I, Q, ev, threads=4)["audio"]
+    monkeypatch.setenv("SDR_MAP_SEARCH", "1")  # plan at every call
+    h = A.SdrBatch(40, _lib=emu_lib)
+    h.configure([(e[0], e[2]) + tuple(e[3:]) for e in ev])
+    got = np.empty((40, 20 * 128), np.float32)
+    b0 = 0
+    for k, nb in enumerate((3, 5, 1, 4, 7)):
+        monkeypatch.setenv("SDR_ALS_SPLIT", str(k & 1))
+        out = np.empty((40, nb * 128), np.float32)
+        h.process_host(np.ascontiguousarray(I[:, b0 * 128:(b0 + nb) * 128]), np.ascontiguousarray(Q[:, b0 * 128:(b0 + nb) * 128]), out)
+        got[:, b0 * 128:(b0 + nb) * 128] = out
+        b0 += nb
+    assert harness.bits_equal(got, want), harness.describe_mismatch(got, want)
+
+
 CONTRACT_TOL = 1e-4  # north_star: max abs error of full scale for the full chain
 
 

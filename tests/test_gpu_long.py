@@ -22,8 +22,10 @@ def dev(cuda_lib):
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("cfg", [2, 3, 4])
-def test_cuda_ten_seconds_sampled_channels(cuda_lib, oracle, dev, cfg):
+@pytest.mark.parametrize("cfg", [2, 3, 4, "4-split"])
+def test_cuda_ten_seconds_sampled_channels(cuda_lib, oracle, dev, monkeypatch, cfg):
+    if cfg == "4-split":  # the two-launch form of the ALS buckets, which the 16 384-channel batch runs on
+        monkeypatch.setenv("SDR_ALS_SPLIT", "1"); cfg = 4
     picks = S.sample_channels(cfg, S.CONFIG_CHANNELS[cfg], 64)
     assert len(picks) >= 64 and {S.channel_mode(cfg, c) for c in picks} == {S.channel_mode(cfg, c) for c in range(4096)}
     I, Q, ev = S.make(cfg, picks, S.BLOCKS_10S)

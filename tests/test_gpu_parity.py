@@ -227,6 +227,56 @@ def test_cuda_als_edge_parameters(cuda_lib, oracle, dev):
     assert_same(a, o["audio"])
 
 
+@pytest.mark.parametrize("case", ["config4", "edge", "sliced", "sam"])
+def test_cuda_split_als_bucket(cuda_lib, oracle, dev, monkeypatch, case):
+    """ALS buckets as two launches (the chain up to the AGC into a scratch plane, then the one-warp ALS + output post-pass):
+    forced here at small channel counts; the 16 384-channel case of test_cuda_full_channel_count_sampled takes it by itself."""
+    from test_emu_pipeline import ALS_EDGE_PARAMS, als_edge_events
+    monkeypatch.setenv("SDR_ALS_SPLIT", "1")
+    chunks = (17, 1, 40)
+    if case == "config4":
+        I, Q, ev = S.make(4, list(range(140)), 90); chunks = (17, 1, 72)
+    elif case == "edge":
+        nch = 4 * len(ALS_EDGE_PARAMS) + 3
+        I, Q, ev = S.make(4, list(range(nch)), 60)
+        ev = [e for e in ev if not e[2].startswith("setALSfilterParams")] + als_edge_events(nch)
+        chunks = (3, 1, 40, 16)
+    elif case == "sliced":  # 1 MB of scratch: slices of 16 to 21 blocks
+        monkeypatch.setenv("SDR_ALS_SCRATCH_MB", "1")
+        I, Q, ev = S.make(4, list(range(70)), 100); chunks = (100,)
+    else:  # SAM + ALS, the chain on the merged 7-warp plan
+        monkeypatch.setenv("SDR_TILE_ENV", "16"); monkeypatch.setenv("SDR_CTAS_PER_SM", "3"); monkeypatch.setenv("SDR_IN_DEPTH", "1")
+        I, Q, ev = S.make(3, list(range(70)), 60); chunks = (17, 1, 42)
+        ev += [(c, 0, "enableALSfilter") for c in range(70)] + [(c, 0, "setALSfilterNotch" if c % 2 else "setALSfilterPeak") for c in range(70)]
+    o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
+    a, b = harness.run_batch(cuda_lib, I, Q, ev, chunks=chunks, device=dev, return_batch=True)
+    assert_same(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+    p = harness.run_batch(cuda_lib, I, Q, ev, chunks=(sum(chunks),), out_dtype=np.int16, device=dev)
+    assert np.array_equal(p, o["pcm"])
+
+
+def test_cuda_als_forms_alternate_between_calls(cuda_lib, oracle, dev, monkeypatch):
+    """One-launch and two-launch form of an ALS bucket from call to call on one handle: same state words, same bits."""
+    import torch
+    import audiosdr_b200 as A
+    I, Q, ev = S.make(4, list(range(100)), 60)
+    want = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)["audio"]
+    monkeypatch.setenv("SDR_MAP_SEARCH", "1")  # plan at every call
+    h = A.SdrBatch(100, _lib=cuda_lib)
+    h.configure([(e[0], e[2]) + tuple(e[3:]) for e in ev])
+    dI, dQ = torch.from_numpy(I).to(dev), torch.from_numpy(Q).to(dev)
+    out = torch.empty((100, 60 * 128), dtype=torch.float32, device=dev)
+    b0 = 0
+    for k, nb in enumerate((3, 25, 1, 4, 27)):
+        monkeypatch.setenv("SDR_ALS_SPLIT", str(k & 1))
+        sl = slice(b0 * 128, (b0 + nb) * 128)
+        h.process(dI[:, sl].contiguous(), dQ[:, sl].contiguous(), out[:, sl], n_blocks=nb)
+        b0 += nb
+    torch.cuda.synchronize()
+    assert_same(out.cpu().numpy(), want)
+
+
 def test_cuda_inrange_divide_equals_ieee_divide(cuda_lib):
     """div_inrange (the SAM PLL's division: fast path without range check / slow-path branch) == IEEE divide for 2^30
     operand pairs covering every exponent pair of [2^-60, 2^60], both signs, powers of two and their neighbours."""
