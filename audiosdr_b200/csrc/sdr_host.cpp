@@ -142,10 +142,12 @@ struct Bucket {
   bool split; SdrLay lay_main, lay_als;
 };
 
+enum { SDR_MAX_BUCKETS = 12 }; /* SSB class: blanker x ALS = 4; ENV class: blanker x ALS x SAM-only = 8 */
+
 struct sdr_batch {
   sdr_batch_desc desc;
   std::vector<Bucket> buckets;
-  void *s_aux[8]; void *ev_fork, *ev_join[8]; /* buckets beyond the first run on their own streams, forked from / joined to the caller's */
+  void *s_aux[SDR_MAX_BUCKETS]; void *ev_fork, *ev_join[SDR_MAX_BUCKETS]; /* buckets beyond the first run on their own streams, forked from / joined to the caller's */
   uint32_t n_ch; size_t ch_stride;
   std::vector<Shadow> sh;
   std::vector<uint32_t> pend_reset; /* per channel SDRK_R_* bits to replay before the next block */
@@ -162,7 +164,7 @@ struct sdr_batch {
   void *d_in_i[2], *d_in_q[2], *d_out[2]; size_t stage_in_bytes, stage_out_bytes;
   void *s_h2d, *s_comp, *s_d2h; void *ev_h2d[2], *ev_comp[2], *ev_d2h[2];
   uint32_t n_groups;
-  float *d_raw[9]; size_t raw_cap[9]; /* scratch planes of split ALS buckets (by bucket index), grown on demand */
+  float *d_raw[SDR_MAX_BUCKETS]; size_t raw_cap[SDR_MAX_BUCKETS]; /* scratch planes of split ALS buckets (by bucket index), grown on demand */
   unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
   std::vector<uint64_t> prof_busy, prof_total, prof_groups, prof_extra, prof_load, prof_crit, prof_bar; /* folded per class */
   uint64_t blocks_done, launches;
@@ -311,7 +313,7 @@ int env_int(const char *name, int dflt) { const char *e = getenv(name); return e
 /* Tile length and shared-memory budget of a bucket.  A group's time does not depend on how many other groups run, so
  * when a launch has more groups than SMs the plan trades ring slack for co-residency: shorter tiles shrink every ring
  * that is sized in tiles.  (SDR_TILE_SSB / SDR_TILE_ENV / SDR_CTAS_PER_SM / SDR_SLACK override the choice for experiments.) */
-int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
+int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm, uint32_t handle_groups) {
   /* Measured: the SSB class is bound by its four Hilbert warps per SM whatever the tile length, so it
    * stays on the 32-sample plan; an ENV group is bound by the latency of its one PLL warp, so ENV buckets without blanker
    * and ALS run 16-sample tiles in a fraction of the shared memory -- two groups per SM; SAM-only buckets with the light
@@ -350,13 +352,14 @@ int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm) {
     if (const char *e = getenv("SDR_MAP_ENV_LEAN")) m = strtoull(e, nullptr, 16);
     lay_place(&b.lay, m);
   } else if (const char *e = getenv("SDR_MAP_SSB_LEAN")) lay_place(&b.lay, strtoull(e, nullptr, 16));
-  /* ALS buckets: one launch while every group has an SM to itself (the ALS warp then runs beside the chain at no cost in
-   * waves); two launches beyond that.  SDR_ALS_SPLIT=0 / 1 forces one form (tests, A/B runs). */
+  /* ALS buckets: one launch while every group of the handle has an SM to itself (the ALS warp then runs beside the chain at
+   * no cost in waves); two launches beyond that (the buckets of a handle run side by side and share the SMs, so the handle's
+   * group count decides).  SDR_ALS_SPLIT=0 / 1 forces one form (tests, A/B runs). */
   b.split = false;
   const int sp = env_int("SDR_ALS_SPLIT", -1);
-  if ((feat & LF_ALS) && sp != 0 && (b.count > (uint32_t)n_sm || sp == 1)) {
+  if ((feat & LF_ALS) && sp != 0 && (handle_groups > (uint32_t)n_sm || sp == 1)) {
     Bucket m; m.first = b.first; m.count = b.count;
-    if (plan_bucket(m, cls, feat & ~(uint32_t)LF_ALS, n_sm) == 0 && lay_build_als(&b.lay_als) == 0) { b.lay_main = m.lay; b.split = true; }
+    if (plan_bucket(m, cls, feat & ~(uint32_t)LF_ALS, n_sm, handle_groups) == 0 && lay_build_als(&b.lay_als) == 0) { b.lay_main = m.lay; b.split = true; }
   }
   return 0;
 }
@@ -399,11 +402,14 @@ int build_groups(sdr_batch *h) {
       flush();
       b.count = (uint32_t)h->h_groups.size() - b.first;
       if (!b.count) continue;
-      if (plan_bucket(b, cls, feat, 148)) return fail(SDR_ERR_UNSUPPORTED, "no shared-memory plan for a bucket (internal)");
+      b.lay.cls = cls; b.lay.feat = feat; /* planned below, when the handle's group count is known */
       h->buckets.push_back(b);
     }
   }
   h->n_groups = (uint32_t)h->h_groups.size();
+  if (h->buckets.size() > (size_t)SDR_MAX_BUCKETS) return fail(SDR_ERR_UNSUPPORTED, "more buckets than SDR_MAX_BUCKETS (internal)");
+  for (Bucket &b : h->buckets)
+    if (plan_bucket(b, b.lay.cls, b.lay.feat, 148, h->n_groups)) return fail(SDR_ERR_UNSUPPORTED, "no shared-memory plan for a bucket (internal)");
   return 0;
 }
 
@@ -534,10 +540,10 @@ void sdr_batch_destroy(sdr_batch_t *h) {
     dev_event_destroy(h->ev_h2d[k]); dev_event_destroy(h->ev_comp[k]); dev_event_destroy(h->ev_d2h[k]);
   }
   dev_stream_destroy(h->s_h2d); dev_stream_destroy(h->s_comp); dev_stream_destroy(h->s_d2h);
-  for (int k = 0; k < 8; k++) { if (h->s_aux[k]) dev_sync(h->s_aux[k]); dev_stream_destroy(h->s_aux[k]); dev_event_destroy(h->ev_join[k]); }
+  for (int k = 0; k < SDR_MAX_BUCKETS; k++) { if (h->s_aux[k]) dev_sync(h->s_aux[k]); dev_stream_destroy(h->s_aux[k]); dev_event_destroy(h->ev_join[k]); }
   dev_event_destroy(h->ev_fork);
   dev_free(h->d_prof);
-  for (int k = 0; k < 9; k++) dev_free(h->d_raw[k]);
+  for (int k = 0; k < SDR_MAX_BUCKETS; k++) dev_free(h->d_raw[k]);
   delete h;
 }
 
@@ -557,8 +563,8 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->s_h2d = h->s_comp = h->s_d2h = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0;
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
-  for (int k = 0; k < 9; k++) { h->d_raw[k] = nullptr; h->raw_cap[k] = 0; }
-  h->ev_fork = nullptr; for (int k = 0; k < 8; k++) { h->s_aux[k] = nullptr; h->ev_join[k] = nullptr; }
+  for (int k = 0; k < SDR_MAX_BUCKETS; k++) { h->d_raw[k] = nullptr; h->raw_cap[k] = 0; }
+  h->ev_fork = nullptr; for (int k = 0; k < SDR_MAX_BUCKETS; k++) { h->s_aux[k] = nullptr; h->ev_join[k] = nullptr; }
   { const char *e = getenv("SDR_ROLE_PROFILE"); h->prof_on = e && e[0] == '1'; }
   h->prof_busy.assign(2 * SDR_STAGES, 0); h->prof_crit.assign(32, 0); h->prof_bar.assign(2 * SDR_STAGES, 0); h->prof_extra.assign(16, 0); h->prof_load.assign(2 * (SDR_STAGES + 1), 0); h->prof_total.assign(2, 0); h->prof_groups.assign(2, 0);
 
@@ -659,7 +665,7 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
   if (nbk > 1) {
     if (!h->ev_fork) {
       if (dev_event_create(&h->ev_fork)) return SDR_ERR_CUDA;
-      for (int k = 0; k < 8; k++) if (dev_stream_create(&h->s_aux[k]) || dev_event_create(&h->ev_join[k])) return SDR_ERR_CUDA;
+      for (int k = 0; k < SDR_MAX_BUCKETS; k++) if (dev_stream_create(&h->s_aux[k]) || dev_event_create(&h->ev_join[k])) return SDR_ERR_CUDA;
     }
     if (dev_event_record(h->ev_fork, stream)) return SDR_ERR_CUDA;
   }
@@ -683,7 +689,7 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
         else show(b.lay, "launch");
       }
     }
-    if (b.split && !h->prof_on && k < 9) {
+    if (b.split && !h->prof_on) {
       /* two launches per slice of the call; the scratch plane holds one slice (SDR_ALS_SCRATCH_MB bounds it, 4 GB by default:
        * a slice is then 2 048 blocks of 16 384 channels, long enough that the state reload per slice does not show) */
       const size_t per_block = (size_t)b.count * SDR_BLOCK_SAMPLES * SDR_LANES * sizeof(float);
@@ -705,6 +711,7 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
         SdrLaunch A = M;
         M.lay = b.lay_main; M.n_tiles = nb * (uint32_t)b.lay_main.tpb; M.flags |= SDRL_RAW_OUT;
         A.lay = b.lay_als; A.n_tiles = nb * (uint32_t)b.lay_als.tpb;
+        A.lay.smem_bytes += env_int("SDR_ALS_PASS_PAD", 0); /* experiment: fewer groups per SM in the post-pass */
         int e = sdrk_launch_pipeline(&M, s);
         if (!e) e = sdrk_launch_als_pass(&A, s);
         if (e) return fail(SDR_ERR_CUDA, "pipeline kernel launch failed (error " + std::to_string(e) + ")");

@@ -310,6 +310,35 @@ def test_emulated_split_als_bucket(oracle, emu_lib, monkeypatch, case, sched):
     assert np.array_equal(p, o["pcm"])
 
 
+def every_bucket_case(nblk=12):
+    """One handle with every kind of bucket at once: USB / AM / SAM channels x blanker on/off x ALS on/off = 12 launches on 12
+    streams per call."""
+    modes = [S.USB, S.AM, S.SAM]
+    chans = [(m, nb, als) for m in modes for nb in (0, 1) for als in (0, 1)]
+    src = {S.USB: 2, S.AM: 4, S.SAM: 3}
+    I = np.empty((len(chans), nblk * 128), np.int16); Q = np.empty_like(I)
+    ev = []
+    for c, (m, nb, als) in enumerate(chans):
+        cfg = src[m]
+        pick = next(k for k in range(4096) if S.channel_mode(cfg, k) == m)
+        i, q, _ = S.make(cfg, [pick], nblk)
+        I[c], Q[c] = i[0], q[0]
+        ev += [(c, 0, "setDemodMode", m), (c, 0, "setAGCmode", S.AGC_MEDIUM), (c, 0, "enableAudioFilter"), (c, 0, "setMute", 0)]
+        ev += [(c, 0, "enableNoiseBlanker" if nb else "disableNoiseBlanker"), (c, 0, "setNoiseBlankerThresholdDb", 10.0)]
+        ev += [(c, 0, "enableALSfilter" if als else "disableALSfilter")]
+    return I, Q, ev
+
+
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_emulated_every_bucket_kind_in_one_handle(oracle, emu_lib, monkeypatch, split):
+    monkeypatch.setenv("SDR_ALS_SPLIT", split)
+    I, Q, ev = every_bucket_case()
+    o = oracle.run(I, Q, ev, threads=4)
+    a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(5, 7), return_batch=True)
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+
+
 def test_emulated_als_forms_alternate_between_calls(oracle, emu_lib, monkeypatch):
     """The one-launch and the two-launch form of an ALS bucket keep the same state words: a handle may change form from call
     to call (the plan is made again whenever the grouping changes)."""

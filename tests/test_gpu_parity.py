@@ -256,6 +256,18 @@ def test_cuda_split_als_bucket(cuda_lib, oracle, dev, monkeypatch, case):
     assert np.array_equal(p, o["pcm"])
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_cuda_every_bucket_kind_in_one_handle(cuda_lib, oracle, dev, monkeypatch, split):
+    """12 buckets = 12 launches on 12 forked streams per call (USB / AM / SAM x blanker x ALS)."""
+    from test_emu_pipeline import every_bucket_case
+    monkeypatch.setenv("SDR_ALS_SPLIT", split)
+    I, Q, ev = every_bucket_case(40)
+    o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
+    a, b = harness.run_batch(cuda_lib, I, Q, ev, chunks=(5, 35), device=dev, return_batch=True)
+    assert_same(a, o["audio"])
+    assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
+
+
 def test_cuda_als_forms_alternate_between_calls(cuda_lib, oracle, dev, monkeypatch):
     """One-launch and two-launch form of an ALS bucket from call to call on one handle: same state words, same bits."""
     import torch
