@@ -1,7 +1,7 @@
 /* sdr_als_pass.cu -- the ALS + output post-pass of a split ALS bucket (sdr_lay.h, lay_build_als).
  *
- * One warp per group (lane = channel), one CTA per warp, 49.5 KB of shared memory: four groups per SM, every one on an SM
- * sub-partition scheduler of its own.  The warp is the chain's output stage (RoleOut: LMS line enhancer C:324-352, output
+ * One warp per group (lane = channel), one CTA per warp, a quarter of an SM's shared memory or less: four groups per SM,
+ * every one on an SM sub-partition scheduler of its own.  The warp is the chain's output stage (RoleOut: LMS line enhancer C:324-352, output
  * gain / mute / truncation C:160, staging rows, row-major stores) fed from the scratch plane the bucket's first launch wrote
  * instead of from the AGC stage's ring: tile t + 1 is requested (asynchronous copies) before tile t is swept, so its 4 KB are
  * in shared memory long before they are needed.  Same arithmetic, same state words as the single-launch form: a handle may
@@ -34,7 +34,7 @@ extern "C" __global__ void __launch_bounds__(32, 8) sdr_als_pass_kernel(const __
     __syncwarp(); /* every lane's share of tile t is in; every lane is done with tile t - 1 */
     if (t + 1 < n) RoleAlsIn::request(x, lane, t + 1, Slots::next(x.k.c, x.nc()));
     cp_async_commit();
-    r.step_a(x, lane, t);
+    if (x.Y->als_mirror) r.step_a<true>(x, lane, t); else r.step_a<false>(x, lane, t);
     __syncwarp();
     r.step_b(x, lane, t);
     __syncwarp();

@@ -359,7 +359,7 @@ int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm, uint32_t handle_gro
   const int sp = env_int("SDR_ALS_SPLIT", -1);
   if ((feat & LF_ALS) && sp != 0 && (handle_groups > (uint32_t)n_sm || sp == 1)) {
     Bucket m; m.first = b.first; m.count = b.count;
-    if (plan_bucket(m, cls, feat & ~(uint32_t)LF_ALS, n_sm, handle_groups) == 0 && lay_build_als(&b.lay_als) == 0) { b.lay_main = m.lay; b.split = true; }
+    if (plan_bucket(m, cls, feat & ~(uint32_t)LF_ALS, n_sm, handle_groups) == 0) { b.lay_main = m.lay; b.split = true; } /* (lay_als: build_groups) */
   }
   return 0;
 }
@@ -408,8 +408,21 @@ int build_groups(sdr_batch *h) {
   }
   h->n_groups = (uint32_t)h->h_groups.size();
   if (h->buckets.size() > (size_t)SDR_MAX_BUCKETS) return fail(SDR_ERR_UNSUPPORTED, "more buckets than SDR_MAX_BUCKETS (internal)");
-  for (Bucket &b : h->buckets)
+  for (Bucket &b : h->buckets) {
     if (plan_bucket(b, b.lay.cls, b.lay.feat, 148, h->n_groups)) return fail(SDR_ERR_UNSUPPORTED, "no shared-memory plan for a bucket (internal)");
+    if (b.split) { /* the post-pass keeps as many taps and as much input history as the bucket's channels ask for (C:393-398) */
+      int m_max = 0, reach_max = 0;
+      for (uint32_t g = b.first; g < b.first + b.count; g++)
+        for (int l = 0; l < SDR_LANES; l++) {
+          const int c = h->h_groups[g].cid[l];
+          if (c < 0 || !(h->h_cfg[c].flags & CF_ALS)) continue;
+          m_max = std::max(m_max, (int)h->h_cfg[c].als_m); reach_max = std::max(reach_max, (int)h->h_cfg[c].als_m + (int)h->h_cfg[c].als_delay);
+        }
+      if (env_int("SDR_ALS_FULL_ROWS", 0)) { m_max = 128; reach_max = 129; } /* experiment / tests: the largest plan whatever the parameters */
+      if (lay_build_als(&b.lay_als, m_max, reach_max)) return fail(SDR_ERR_UNSUPPORTED, "no plan for the ALS post-pass (internal)");
+      if (env_int("SDR_ALS_NO_MIRROR", 0) && b.lay_als.als_mirror) { b.lay_als.als_mirror = 0; b.lay_als.smem_bytes -= b.lay_als.nc * b.lay_als.tile_f * 4; }
+    }
+  }
   return 0;
 }
 

@@ -327,26 +327,38 @@ static inline int lay_build(SdrLay *L, int cls, uint32_t feat, int T, int budget
 
 /* The ALS + output post-pass (SdrLay::cls == CLS_ALS).  The LMS line enhancer (C:324-352) is the chain's last stage and by far
  * its slowest (one warp sweeps 55 taps for every 4 samples, each sweep waiting for the error of the sweep before), and a
- * group that carries it fills an SM's shared memory, so a bucket with more groups than SMs queues in waves whose length the
- * ALS warp sets.  Such a bucket runs in two launches instead: the chain up to the AGC -- the bucket's plan without ALS, its
- * output stage writing the AGC output tiles as they are to a scratch plane (SdrLaunch::flags & SDRL_RAW_OUT) -- and this
- * plan: ONE warp per group that fetches the scratch tiles one tile ahead (asynchronous copies straight into the ALS input
- * ring: the scratch plane has the ring's [sample][lane] layout) and runs the chain's ALS + output stage unchanged.  49.5 KB
- * per group: four groups share an SM, each on a scheduler of its own, and 592 groups run at once.
- * Ring: the sweep for a tile reaches back M + delay <= 129 samples and loads (without using) up to 9 more; with 7 slots the
- * slot being filled one tile ahead is never one a sweep touches.  A single warp in program order: no hand-over rules. */
-static inline int lay_build_als(SdrLay *L) {
+ * group that carries it fills an SM's shared memory, so a handle with more groups than SMs queues in waves whose length the
+ * ALS warp sets.  Such a handle's ALS buckets run in two launches instead: the chain up to the AGC -- the bucket's plan
+ * without ALS, its output stage writing the AGC output tiles as they are to a scratch plane (SdrLaunch::flags &
+ * SDRL_RAW_OUT) -- and this plan: ONE warp per group that fetches the scratch tiles one tile ahead (asynchronous copies
+ * straight into the ALS input ring: the scratch plane has the ring's [sample][lane] layout) and runs the chain's ALS +
+ * output stage.  A quarter of an SM's shared memory or less per group: four groups share an SM, each on a scheduler of its
+ * own.
+ *   m_max, reach_max: the largest tap count M and the largest M + delay among the bucket's channels (C:393-398).
+ * Tap array: the sweeps load taps up to index M + 4 (five are fetched ahead), so M + 5 rows (at most 128) are kept.
+ * Ring: the sweeps for a tile reach back M + delay samples and load (without using) up to 9 more; one more slot holds the
+ * tile being swept and one the tile being fetched: never one a sweep touches.  At least 5 slots: the state keeps 128 samples.
+ * When it fits the quarter SM, the ring is kept TWICE, back to back (every tile is fetched into slot s and slot s + nc):
+ * any run of ring positions is then contiguous in one of the two copies and no sweep ever wraps (als_tile<true>).
+ * A single warp in program order: no hand-over rules. */
+static inline int lay_build_als(SdrLay *L, int m_max, int reach_max) {
   memset(L, 0, sizeof *L);
   const int T = 32, tile_b = T * SDR_LANES * 4;
+  if (m_max < 0) m_max = 0; if (m_max > 128) m_max = 128;
+  if (reach_max < m_max) reach_max = m_max; if (reach_max > 129) reach_max = 129;
   L->cls = CLS_ALS; L->feat = LF_ALS; L->T = T; L->tpb = 4; L->tpb_sh = 2; L->tile_f = T * SDR_LANES;
   L->active[ST_IN] = L->active[ST_OUT] = 1;
   for (int s = 0; s < 16; s++) { L->bar_of[s] = (uint8_t)s; L->bar_count[s] = 1; }
-  L->nr = L->na = L->ni = L->nz = L->nz2 = L->hq_tiles = 1; L->nc = L->tpb + 3; L->ins_row = T + 4; L->in_depth = 1;
+  L->nr = L->na = L->ni = L->nz = L->nz2 = L->hq_tiles = 1; L->ins_row = T + 4; L->in_depth = 1;
+  L->nc = (reach_max + 9 + T - 1) / T + 2; if (L->nc < 5) L->nc = 5;
+  L->als_rows = m_max + 5 > 128 ? 128 : m_max + 5;
+  const int fixed = 128 + L->als_rows * SDR_LANES * 4 + SDR_LANES * L->ins_row * 4;
+  L->als_mirror = fixed + 2 * L->nc * tile_b <= (233472 - 4 * 1024) / 4;
   int o = 0;
   L->o_cid = o; o += 128;
-  L->o_alsc = o; o += 128 * SDR_LANES * 4;
+  L->o_alsc = o; o += L->als_rows * SDR_LANES * 4;
   L->o_outs = o; o += SDR_LANES * L->ins_row * 4;
-  L->o_c = o; o += L->nc * tile_b;
+  L->o_c = o; o += (L->als_mirror ? 2 : 1) * L->nc * tile_b;
   L->smem_bytes = o;
   memset(L->prog, 0xFF, sizeof L->prog);
   L->n_warps = 1; L->prog[0][0] = ST_IN; L->prog[0][1] = ST_OUT; L->stage_of_warp[0] = ST_IN;

@@ -123,6 +123,7 @@ typedef struct {
                                         the Hilbert warps, the two image rails) share one barrier per tile, completed by all their arrivals */
   uint8_t bar_count[16];             /* arrivals that complete a barrier of that stage id */
   int32_t in_depth;                  /* input tiles requested ahead (landing buffers of the IN stage) */
+  int32_t als_rows, als_mirror;      /* ALS post-pass plan (lay_build_als): rows of the tap array kept in shared memory; input ring kept twice */
   int8_t delay[16];                  /* the stage's delay in the lock-step schedule (documentation, deadlock-freedom proof, emulation) */
   SdrDep deps[SDR_STAGES][SDR_MAX_DEPS];
 } SdrLay;

@@ -278,8 +278,21 @@ def test_emulated_short_tile_plans(oracle, emu_lib, monkeypatch, cfg, nch, nblk,
     assert np.array_equal(harness.status_matrix(b), o["status"], equal_nan=True)
 
 
+ALS_SMALL_PARAMS = [(55, 0.5, 3), (86, 0.3, 1), (1, 0.5, 0), (4, 0.6, 1), (60, 0.5, 27), (85, 0.25, 0), (33, 0.5, 54)]
+
+
+def als_small_events(nch):
+    """ALS parameters within what the post-pass keeps in a quarter of an SM with its input ring doubled (M <= 86, M + delay <= 87)."""
+    ev = []
+    for c in range(nch):
+        m, lam, d = ALS_SMALL_PARAMS[c % len(ALS_SMALL_PARAMS)]
+        ev += [(c, 0, "setALSfilterParams", m, lam, d), (c, 0, "enableALSfilter"), (c, 0, "setALSfilterAdaptive" if c % 5 else "setALSfilterStatic")]
+        ev += [(c, 0, "setALSfilterNotch" if c % 2 else "setALSfilterPeak")]
+    return ev
+
+
 @pytest.mark.parametrize("sched", ["lockstep", "lockstep-reversed", "consumers", "random:4/late"])
-@pytest.mark.parametrize("case", ["config4", "edge", "sliced", "sam"])
+@pytest.mark.parametrize("case", ["config4", "edge", "sliced", "sam", "small", "small-single-ring", "config4-largest-plan"])
 def test_emulated_split_als_bucket(oracle, emu_lib, monkeypatch, case, sched):
     """A bucket with the ALS filter and more groups than SMs runs as two launches -- the chain up to the AGC into a scratch
     plane, then the ALS + output post-pass (sdr_lay.h, lay_build_als): same bits, whatever plan the chain runs on, also when
@@ -294,6 +307,16 @@ def test_emulated_split_als_bucket(oracle, emu_lib, monkeypatch, case, sched):
         I, Q, ev = S.make(4, list(range(nch)), 14)
         ev = [e for e in ev if not e[2].startswith("setALSfilterParams")] + als_edge_events(nch)
         chunks = (3, 1, 6, 4)
+    elif case.startswith("small"):  # doubled input ring (no sweep wraps) with every kind of tap count / delay it admits; the same on a single ring
+        if case == "small-single-ring":
+            monkeypatch.setenv("SDR_ALS_NO_MIRROR", "1")
+        nch = 3 * len(ALS_SMALL_PARAMS)
+        I, Q, ev = S.make(4, list(range(nch)), 14)
+        ev = [e for e in ev if not e[2].startswith("setALSfilterParams")] + als_small_events(nch)
+        chunks = (3, 1, 6, 4)
+    elif case == "config4-largest-plan":  # all 128 tap rows and the deepest ring although the channels use the defaults
+        monkeypatch.setenv("SDR_ALS_FULL_ROWS", "1")
+        I, Q, ev = S.make(4, list(range(70)), 24)
     elif case == "sliced":  # 3 groups: 48 KB of scratch per block, 1 MB holds 21 blocks -> the 40-block call runs as two slices
         monkeypatch.setenv("SDR_ALS_SCRATCH_MB", "1")
         I, Q, ev = S.make(4, list(range(20)), 40)

@@ -227,11 +227,11 @@ def test_cuda_als_edge_parameters(cuda_lib, oracle, dev):
     assert_same(a, o["audio"])
 
 
-@pytest.mark.parametrize("case", ["config4", "edge", "sliced", "sam"])
+@pytest.mark.parametrize("case", ["config4", "edge", "sliced", "sam", "small", "small-single-ring", "config4-largest-plan"])
 def test_cuda_split_als_bucket(cuda_lib, oracle, dev, monkeypatch, case):
     """ALS buckets as two launches (the chain up to the AGC into a scratch plane, then the one-warp ALS + output post-pass):
     forced here at small channel counts; the 16 384-channel case of test_cuda_full_channel_count_sampled takes it by itself."""
-    from test_emu_pipeline import ALS_EDGE_PARAMS, als_edge_events
+    from test_emu_pipeline import ALS_EDGE_PARAMS, ALS_SMALL_PARAMS, als_edge_events, als_small_events
     monkeypatch.setenv("SDR_ALS_SPLIT", "1")
     chunks = (17, 1, 40)
     if case == "config4":
@@ -241,6 +241,16 @@ def test_cuda_split_als_bucket(cuda_lib, oracle, dev, monkeypatch, case):
         I, Q, ev = S.make(4, list(range(nch)), 60)
         ev = [e for e in ev if not e[2].startswith("setALSfilterParams")] + als_edge_events(nch)
         chunks = (3, 1, 40, 16)
+    elif case.startswith("small"):  # the doubled input ring with every tap count / delay it admits; the same on a single ring
+        if case == "small-single-ring":
+            monkeypatch.setenv("SDR_ALS_NO_MIRROR", "1")
+        nch = 6 * len(ALS_SMALL_PARAMS)
+        I, Q, ev = S.make(4, list(range(nch)), 60)
+        ev = [e for e in ev if not e[2].startswith("setALSfilterParams")] + als_small_events(nch)
+        chunks = (3, 1, 40, 16)
+    elif case == "config4-largest-plan":
+        monkeypatch.setenv("SDR_ALS_FULL_ROWS", "1")
+        I, Q, ev = S.make(4, list(range(140)), 90); chunks = (17, 1, 72)
     elif case == "sliced":  # 1 MB of scratch: slices of 16 to 21 blocks
         monkeypatch.setenv("SDR_ALS_SCRATCH_MB", "1")
         I, Q, ev = S.make(4, list(range(70)), 100); chunks = (100,)
