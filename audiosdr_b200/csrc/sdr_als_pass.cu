@@ -26,7 +26,6 @@ extern "C" __global__ void __launch_bounds__(32, 8) sdr_als_pass_kernel(const __
   x.k.reset();
   RoleOut r; r.load(x, lane);
   const uint32_t n = L.n_tiles;
-  const bool uni = (L.flags & SDRL_ALS_UNIFORM) != 0 && L.lay.als_mirror != 0;
   RoleAlsIn::request(x, lane, 0, 0);
   cp_async_commit();
 #pragma unroll 1
@@ -35,9 +34,7 @@ extern "C" __global__ void __launch_bounds__(32, 8) sdr_als_pass_kernel(const __
     __syncwarp(); /* every lane's share of tile t is in; every lane is done with tile t - 1 */
     if (t + 1 < n) RoleAlsIn::request(x, lane, t + 1, Slots::next(x.k.c, x.nc()));
     cp_async_commit();
-    if (uni) r.step_a<true, true>(x, lane, t); /* the usual case: one ALS setting for the whole bucket, doubled ring */
-    else if (x.Y->als_mirror) r.step_a<true, false>(x, lane, t);
-    else r.step_a<false, false>(x, lane, t);
+    if (x.Y->als_mirror) r.step_a<true>(x, lane, t); else r.step_a<false>(x, lane, t);
     __syncwarp();
     r.step_b(x, lane, t);
     __syncwarp();

@@ -140,7 +140,6 @@ struct Bucket {
   /* a bucket with the ALS filter and more groups than SMs runs as two launches (sdr_lay.h, lay_build_als): the chain up to
    * the AGC on the plan the bucket would have without ALS, then the ALS + output post-pass, four groups to an SM */
   bool split; SdrLay lay_main, lay_als;
-  bool als_uniform; int als_m, als_delay; uint32_t als_flags; /* every channel of the bucket has the same ALS setting (the post-pass then takes it from the launch) */
 };
 
 enum { SDR_MAX_BUCKETS = 12 }; /* SSB class: blanker x ALS = 4; ENV class: blanker x ALS x SAM-only = 8 */
@@ -413,18 +412,13 @@ int build_groups(sdr_batch *h) {
     if (plan_bucket(b, b.lay.cls, b.lay.feat, 148, h->n_groups)) return fail(SDR_ERR_UNSUPPORTED, "no shared-memory plan for a bucket (internal)");
     if (b.split) { /* the post-pass keeps as many taps and as much input history as the bucket's channels ask for (C:393-398) */
       int m_max = 0, reach_max = 0;
-      bool first = true; b.als_uniform = true; b.als_m = b.als_delay = 0; b.als_flags = 0;
       for (uint32_t g = b.first; g < b.first + b.count; g++)
         for (int l = 0; l < SDR_LANES; l++) {
           const int c = h->h_groups[g].cid[l];
           if (c < 0 || !(h->h_cfg[c].flags & CF_ALS)) continue;
           const SdrChanCfg &k = h->h_cfg[c];
-          const uint32_t fl = k.flags & CF_ALS_ADAPT; /* (notch / peak is a select per sample: stays per channel) */
           m_max = std::max(m_max, (int)k.als_m); reach_max = std::max(reach_max, (int)k.als_m + (int)k.als_delay);
-          if (first) { b.als_m = k.als_m; b.als_delay = k.als_delay; b.als_flags = fl; first = false; }
-          else if (k.als_m != b.als_m || k.als_delay != b.als_delay || fl != b.als_flags) b.als_uniform = false;
         }
-      if (env_int("SDR_ALS_NO_UNIFORM", 0)) b.als_uniform = false;
       if (env_int("SDR_ALS_FULL_ROWS", 0)) { m_max = 128; reach_max = 129; } /* experiment / tests: the largest plan whatever the parameters */
       if (lay_build_als(&b.lay_als, m_max, reach_max)) return fail(SDR_ERR_UNSUPPORTED, "no plan for the ALS post-pass (internal)");
       if (env_int("SDR_ALS_NO_MIRROR", 0) && b.lay_als.als_mirror) { b.lay_als.als_mirror = 0; b.lay_als.smem_bytes -= b.lay_als.nc * b.lay_als.tile_f * 4; }
@@ -731,7 +725,6 @@ int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_
         SdrLaunch A = M;
         M.lay = b.lay_main; M.n_tiles = nb * (uint32_t)b.lay_main.tpb; M.flags |= SDRL_RAW_OUT;
         A.lay = b.lay_als; A.n_tiles = nb * (uint32_t)b.lay_als.tpb;
-        if (b.als_uniform) { A.flags |= SDRL_ALS_UNIFORM; A.als_m = b.als_m; A.als_delay = b.als_delay; A.als_flags = b.als_flags; }
         A.lay.smem_bytes += env_int("SDR_ALS_PASS_PAD", 0); /* experiment: fewer groups per SM in the post-pass */
         int e = sdrk_launch_pipeline(&M, s);
         if (!e) e = sdrk_launch_als_pass(&A, s);

@@ -145,7 +145,6 @@ typedef struct {
   uint32_t flags;        /* SDRL_CONTRACT: the handle asked for the contracting build (sdr_batch_desc.flags & SDR_BATCH_CONTRACT);
                             SDRL_RAW_OUT: first launch of a split ALS bucket -- the output stage writes the AGC output as it is (float32, no
                             ALS, gain, mute or truncation) to the scratch plane the ALS post-pass reads */
-  int32_t als_m, als_delay; uint32_t als_flags; /* SDRL_ALS_UNIFORM (post-pass): the tap count, delay and CF_ALS_ADAPT flag every channel of the launch has */
   float *raw;            /* split ALS bucket: scratch plane [group of the launch][sample of the call][lane] (float32), written by the
                             SDRL_RAW_OUT launch, read by the ALS post-pass (sdr_als_pass.cu) */
   uint32_t diag_skip;    /* diagnostics (profiling runs only): bit s set = stage s idles; results are then meaningless */
@@ -153,7 +152,7 @@ typedef struct {
   SdrLay lay;
 } SdrLaunch;
 
-enum { SDRL_CONTRACT = 1u, SDRL_RAW_OUT = 2u, SDRL_ALS_UNIFORM = 4u };
+enum { SDRL_CONTRACT = 1u, SDRL_RAW_OUT = 2u };
 
 /* default placement of the stages on the warps of a CTA (warp id % 4 = SM sub-partition, higher id = preferred by the
  * scheduler) for the launches that run all 14 stages; SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */

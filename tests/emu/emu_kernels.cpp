@@ -179,12 +179,7 @@ int run_als_group(const SdrLaunch &L, const SdrGroup &G, int gidx) {
   for (uint32_t t = 0; t < n; t++) {
     cp_async_wait_pending(0);
     if (t + 1 < n) for (int lane = 0; lane < 32; lane++) RoleAlsIn::request(x, lane, t + 1, Slots::next(x.k.c, Y.nc));
-    const bool uni = (L.flags & SDRL_ALS_UNIFORM) != 0 && Y.als_mirror != 0;
-    for (int lane = 0; lane < 32; lane++) {
-      if (uni) out[lane].step_a<true, true>(x, lane, t);
-      else if (Y.als_mirror) out[lane].step_a<true, false>(x, lane, t);
-      else out[lane].step_a<false, false>(x, lane, t);
-    }
+    for (int lane = 0; lane < 32; lane++) { if (Y.als_mirror) out[lane].step_a<true>(x, lane, t); else out[lane].step_a<false>(x, lane, t); }
     for (int lane = 0; lane < 32; lane++) out[lane].step_b(x, lane, t);
     x.k.advance(x);
   }

@@ -1,6 +1,6 @@
 #!/bin/bash
 # tools/gpu_check_r02.sh [tag] -- the on-box evidence sequence of round 2 (run under gpurun): smoke, GPU tests, both bench arms,
-# ncu launch list + full captures (config 2 and config 3 kernels), sanitizers, aux benches.  Everything lands in gpurun_out/.
+# ncu launch list + full captures (config 2, config 3 and ALS post-pass kernels), sanitizers, aux benches.  Everything lands in gpurun_out/.
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r02}
@@ -33,4 +33,9 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sdr
 echo "== ncu full: config 3 kernel (merged SAM plan, three groups per SM)"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sdr_pipeline -s 3 -c 1 -f -o gpurun_out/${TAG}_pipeline_w3 \
     python bench.py --workload 3 --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline --only-headline > gpurun_out/${TAG}_ncu_full_w3.log 2>&1; echo "ncu full rc=$?"
+echo "== ncu launch list + full capture: config 4 (ALS buckets as two launches; the post-pass kernel)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sdr_ -c 60 --csv --log-file gpurun_out/${TAG}_launches_w4.csv \
+    python bench.py --workload 4 --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --only-headline > gpurun_out/${TAG}_ncu_launch_w4.log 2>&1; echo "ncu list rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sdr_als_pass -s 3 -c 1 -f -o gpurun_out/${TAG}_als_pass \
+    python bench.py --workload 4 --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline --only-headline > gpurun_out/${TAG}_ncu_full_w4.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out | grep ${TAG}_ | head -40
