@@ -153,7 +153,11 @@ int sdr_batch_set(sdr_batch_t *h, const uint32_t *channel_ids, uint32_t n, uint3
 int sdr_batch_configure(sdr_batch_t *h, const sdr_setter_call *calls, uint32_t n_calls);
 
 /* The hot path.  Device pointers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).
- * in_fmt/out_fmt: SDR_FMT_*; pitches in elements.  Advances every channel by n_blocks blocks. */
+ * in_fmt/out_fmt: SDR_FMT_*; pitches in elements.  Advances every channel by n_blocks blocks.
+ * Device memory the handle owns besides the 7.9 KB of state per channel: a handle with more than 148 groups of 32
+ * channels (4 736 channels or fewer, by mode mix) keeps a scratch plane for those that use the ALS filter, 4 bytes per ALS
+ * channel and sample of the longest call so far, at most SDR_ALS_SCRATCH_MB (environment, default 4096) megabytes per kind
+ * of channel (run-time switches). */
 int sdr_batch_process_device(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt,
                              void *audio, size_t out_pitch, int out_fmt, uint32_t n_blocks, void *cuda_stream);
 /* The same call in its plainest form: float32 planes, rows densely packed (pitch = 128 * n_blocks elements). */
