@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdr_batch.so")
-SOURCES = ["sdr_kernel.cu", "sdr_pipe_t32.cu", "sdr_pipe_t16.cu", "sdr_pipe_t8.cu", "sdr_pipe_t32c.cu", "sdr_als_pass.cu", "sdr_host.cpp"]
+SOURCES = ["sdr_kernel.cu", "sdr_pipe_t32.cu", "sdr_pipe_t16.cu", "sdr_pipe_t8.cu", "sdr_pipe_t32c.cu", "sdr_pipe_t32s.cu", "sdr_als_pass.cu", "sdr_host.cpp"]
 DEPS = SOURCES + ["sdr_pipeline.cuh", "sdr_pipe_tu.cuh", "sdr_lay.h", "sdr_types.h", "sdr_kernel.h", "sdr_tables.inc", os.path.join("..", "..", "include", "sdr_batch.h")]
 
 # -fmad=false: the reference rounds every product and every sum separately (x86-64 SSE, no FMA); contraction
@@ -37,7 +37,7 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     # SDR_NVCC_EXTRA: extra -D switches for A/B builds of kernel variants (tools/gpu_ab.sh); unset for the product
-    cmd = [_nvcc()] + NVCC_FLAGS + ["--threads", "4"] + os.environ.get("SDR_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else [])
+    cmd = [_nvcc()] + NVCC_FLAGS + ["--threads", "8"] + os.environ.get("SDR_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else [])
     # sdr_host.cpp is plain C++ that calls the CUDA runtime: compile it as CUDA so that one nvcc call links everything
     for src in SOURCES:
         cmd += ["-x", "cu", os.path.join(CSRC, src)]

@@ -8,6 +8,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "sdr_kernel.h"
 #include "sdr_pipeline.cuh"
@@ -18,6 +19,7 @@ extern "C" {
 int sdrk_setup_pipe_t32(const float *), sdrk_setup_pipe_t16(const float *), sdrk_setup_pipe_t8(const float *), sdrk_setup_pipe_t32c(const float *);
 int sdrk_launch_pipe_t32(const SdrLaunch *, void *), sdrk_launch_pipe_t16(const SdrLaunch *, void *), sdrk_launch_pipe_t8(const SdrLaunch *, void *);
 int sdrk_launch_pipe_t32c(const SdrLaunch *, void *);
+int sdrk_setup_pipe_t32s(const float *), sdrk_launch_pipe_t32s(const SdrLaunch *, void *), sdrk_occupancy_t32s(const SdrLaunch *);
 int sdrk_occupancy_t32(const SdrLaunch *), sdrk_occupancy_t16(const SdrLaunch *), sdrk_occupancy_t8(const SdrLaunch *);
 int sdrk_setup_als_pass(void), sdrk_occupancy_als_pass(const SdrLaunch *); /* sdr_als_pass.cu */
 }
@@ -83,13 +85,18 @@ extern "C" int sdrk_setup_device(const float *hilbert64) {
   if (!e) e = sdrk_setup_pipe_t16(hilbert64);
   if (!e) e = sdrk_setup_pipe_t8(hilbert64);
   if (!e) e = sdrk_setup_pipe_t32c(hilbert64);
+  if (!e) e = sdrk_setup_pipe_t32s(hilbert64);
   if (!e) e = sdrk_setup_als_pass();
   return e;
 }
 
 extern "C" int sdrk_launch_pipeline(const SdrLaunch *L, void *stream) {
   if (L->n_groups == 0) return 0;
-  if (L->lay.T == 32) return (L->flags & 1u) ? sdrk_launch_pipe_t32c(L, stream) : sdrk_launch_pipe_t32(L, stream);
+  if (L->lay.T == 32) {
+    if (L->flags & SDRL_CONTRACT) return sdrk_launch_pipe_t32c(L, stream);
+    static const bool general = [] { const char *e = getenv("SDR_NO_CLASS_KERNEL"); return e && e[0] == '1'; }(); /* A/B switch */
+    return L->lay.cls == CLS_SSB && !general ? sdrk_launch_pipe_t32s(L, stream) : sdrk_launch_pipe_t32(L, stream);
+  }
   if (L->lay.T == 16) return sdrk_launch_pipe_t16(L, stream);
   if (L->lay.T == 8) return sdrk_launch_pipe_t8(L, stream);
   return 1;
@@ -97,7 +104,7 @@ extern "C" int sdrk_launch_pipeline(const SdrLaunch *L, void *stream) {
 
 extern "C" int sdrk_occupancy(const SdrLaunch *L) {
   if (L->lay.cls == CLS_ALS) return sdrk_occupancy_als_pass(L);
-  return L->lay.T == 32 ? sdrk_occupancy_t32(L) : (L->lay.T == 16 ? sdrk_occupancy_t16(L) : sdrk_occupancy_t8(L));
+  return L->lay.T == 32 ? (L->lay.cls == CLS_SSB ? sdrk_occupancy_t32s(L) : sdrk_occupancy_t32(L)) : (L->lay.T == 16 ? sdrk_occupancy_t16(L) : sdrk_occupancy_t8(L));
 }
 
 extern "C" int sdrk_launch_reset(float *state, unsigned long long ch_stride, const uint32_t *chan, const uint32_t *mask, uint32_t n,

@@ -196,7 +196,7 @@ __device__ __forceinline__ void pipeline_loop(const Ctx &x, int stage, Body body
  * values of the launch's plan) to keep the kernel's instruction footprint small: every warp runs different code, so
  * the hot loops of all stages have to share the instruction caches. */
 __device__ __forceinline__ void run_stage(const Ctx &x, int stage, int lane) {
-  const bool ssb = x.Y->cls == CLS_SSB;
+  const bool ssb = x.cls() == CLS_SSB;
   if (!x.Y->active[stage]) { pipeline_loop(x, stage, [&](uint32_t) {}); return; } /* a stage this bucket does not have: keeps step only */
 #if defined(SDR_LOCKSTEP) && SDR_FIXED_T != 32
   if (x.Y->prog[threadIdx.x >> 5][1] != 0xFF) { /* merged plan: this warp runs several stages per step */
