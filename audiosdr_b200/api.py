@@ -29,7 +29,8 @@ SETTERS = dict(
 EXPORTS = ["sdr_batch_create", "sdr_batch_destroy", "sdr_batch_set", "sdr_batch_configure", "sdr_batch_process_device",
            "sdr_batch_process_host", "sdr_batch_get_status", "sdr_batch_get_agc_lookup", "sdr_batch_peek_state",
            "sdr_batch_get_role_profile", "sdr_batch_launch_count", "sdr_batch_last_error", "sdr_batch_version",
-           "sdr_batch_process", "sdr_batch_state_bytes", "sdr_batch_export_state", "sdr_batch_import_state"]
+           "sdr_batch_process", "sdr_batch_state_bytes", "sdr_batch_export_state", "sdr_batch_import_state",
+           "sdr_batch_submit_host", "sdr_batch_wait_host"]
 
 
 class SdrError(RuntimeError):
@@ -70,6 +71,8 @@ def _bind(L):
                                            C.c_size_t, C.c_int, C.c_uint32, C.c_void_p]
     L.sdr_batch_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                          C.c_size_t, C.c_int, C.c_uint32]
+    L.sdr_batch_submit_host.argtypes = L.sdr_batch_process_host.argtypes
+    L.sdr_batch_wait_host.argtypes = [C.c_void_p]
     L.sdr_batch_get_status.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_get_agc_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_peek_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
@@ -273,3 +276,17 @@ class SdrBatch:
                                                   _fmt_of(str(I.dtype)), audio.ctypes.data,
                                                   audio.strides[0] // audio.itemsize, _fmt_of(str(audio.dtype)), n_blocks))
         return audio
+
+    def submit_host(self, I, Q, audio, n_blocks=None):
+        """Streaming form of process_host: queues the call and returns; `wait_host()` completes everything queued.  The arrays
+        must be C-contiguous rows (they are used in place: no copy is made) and should be pinned; I, Q must stay unchanged
+        and `audio` unread until wait_host() returns."""
+        assert I.shape == Q.shape and I.dtype == Q.dtype and I.shape[0] == self.n_channels and audio.shape[0] == self.n_channels
+        assert I.strides[1] == I.itemsize and Q.strides == I.strides and audio.strides[1] == audio.itemsize
+        n_blocks = int(n_blocks if n_blocks is not None else I.shape[1] // N_BLOCK)
+        self._check(self.L.sdr_batch_submit_host(self.h, I.ctypes.data, Q.ctypes.data, I.strides[0] // I.itemsize,
+                                                 _fmt_of(str(I.dtype)), audio.ctypes.data,
+                                                 audio.strides[0] // audio.itemsize, _fmt_of(str(audio.dtype)), n_blocks))
+
+    def wait_host(self):
+        self._check(self.L.sdr_batch_wait_host(self.h))

@@ -163,6 +163,7 @@ struct sdr_batch {
    * the D2H copy of chunk k-1 overlap */
   void *d_in_i[2], *d_in_q[2], *d_out[2]; size_t stage_in_bytes, stage_out_bytes;
   void *s_h2d, *s_comp, *s_d2h; void *ev_h2d[2], *ev_comp[2], *ev_d2h[2];
+  uint64_t host_seq; /* chunks queued by submit_host since create: chunk n uses staging set n & 1 */
   uint32_t n_groups;
   float *d_raw[SDR_MAX_BUCKETS]; size_t raw_cap[SDR_MAX_BUCKETS]; /* scratch planes of split ALS buckets (by bucket index), grown on demand */
   unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
@@ -344,7 +345,8 @@ int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm, uint32_t handle_gro
   if (rc) return rc;
   /* measured placements */
   if (b.lay.n_warps == SDR_STAGES) {
-    unsigned long long m = cls == CLS_SSB ? ((feat & LF_ALS) ? SDR_MAP_SSB_ALS_DEFAULT : SDR_MAP_SSB_DEFAULT) : SDR_MAP_ENV_DEFAULT;
+    unsigned long long m = cls == CLS_SSB ? ((feat & LF_ALS) ? SDR_MAP_SSB_ALS_DEFAULT : (feat & LF_NB) ? SDR_MAP_SSB_DEFAULT : SDR_MAP_SSB_NONB_DEFAULT)
+                                          : SDR_MAP_ENV_DEFAULT;
     if (const char *e = getenv(cls == CLS_SSB ? "SDR_MAP_SSB" : "SDR_MAP_ENV")) m = strtoull(e, nullptr, 16);
     lay_place(&b.lay, m);
   } else if (cls == CLS_ENV && b.lay.n_warps == 11) {
@@ -574,7 +576,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->d_reset_ch = h->d_reset_mask = nullptr; h->reset_cap = h->luts_cap = h->groups_cap = 0;
   h->d_gather = nullptr; h->d_gather_ids = h->d_gather_words = nullptr; h->gather_cap = 0;
   for (int k = 0; k < 2; k++) { h->d_in_i[k] = h->d_in_q[k] = h->d_out[k] = nullptr; h->ev_h2d[k] = h->ev_comp[k] = h->ev_d2h[k] = nullptr; }
-  h->s_h2d = h->s_comp = h->s_d2h = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0;
+  h->s_h2d = h->s_comp = h->s_d2h = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0; h->host_seq = 0;
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   for (int k = 0; k < SDR_MAX_BUCKETS; k++) { h->d_raw[k] = nullptr; h->raw_cap[k] = 0; }
@@ -748,8 +750,23 @@ int sdr_batch_process(sdr_batch_t *h, const float *I, const float *Q, float *aud
   return sdr_batch_process_device(h, I, Q, pitch, SDR_FMT_F32, audio, pitch, SDR_FMT_F32, n_blocks, cuda_stream);
 }
 
+int sdr_batch_wait_host(sdr_batch_t *h) {
+  if (!h) return fail(SDR_ERR_ARG, "wait_host: bad arguments");
+  if (!h->s_comp) return SDR_OK; /* nothing was ever submitted */
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  if (dev_sync(h->s_d2h) | dev_sync(h->s_comp) | dev_sync(h->s_h2d)) return SDR_ERR_CUDA; /* all three are drained either way */
+  return SDR_OK;
+}
+
 int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio,
                            size_t out_pitch, int out_fmt, uint32_t n_blocks) {
+  const int rc = sdr_batch_submit_host(h, I, Q, in_pitch, in_fmt, audio, out_pitch, out_fmt, n_blocks);
+  if (rc) return rc; /* (submit has drained the streams) */
+  return sdr_batch_wait_host(h);
+}
+
+int sdr_batch_submit_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio,
+                          size_t out_pitch, int out_fmt, uint32_t n_blocks) {
   if (!h || !I || !Q || !audio) return fail(SDR_ERR_ARG, "process_host: bad arguments");
   if (n_blocks == 0) return fail(SDR_ERR_ARG, "n_blocks == 0");
   if (in_fmt != SDR_FMT_I16 && in_fmt != SDR_FMT_F32) return fail(SDR_ERR_ARG, "process_host: unknown input format");
@@ -813,17 +830,18 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
   while (done < n_blocks) {
     const uint32_t nb = sizes[k];
     const size_t w_in = (size_t)nb * SDR_BLOCK_SAMPLES * ies, w_out = (size_t)nb * SDR_BLOCK_SAMPLES * oes;
-    const int b = (int)(k & 1);
+    const int b = (int)(h->host_seq & 1); /* the two staging sets keep alternating from call to call */
     const char *srcI = (const char *)I + (size_t)done * SDR_BLOCK_SAMPLES * ies, *srcQ = (const char *)Q + (size_t)done * SDR_BLOCK_SAMPLES * ies;
     char *dst = (char *)audio + (size_t)done * SDR_BLOCK_SAMPLES * oes;
-    /* H2D of chunk k into staging set b: the kernel of chunk k-2 must be done with it */
-    if (k >= 2) { SDR_TRY(dev_stream_wait(h->s_h2d, h->ev_comp[b]) ? SDR_ERR_CUDA : 0); }
+    /* H2D of chunk k into staging set b: the kernel of chunk k-2 (of this call or, with submit_host, of the call before) must
+     * be done with it */
+    if (h->host_seq >= 2) { SDR_TRY(dev_stream_wait(h->s_h2d, h->ev_comp[b]) ? SDR_ERR_CUDA : 0); }
     SDR_TRY(h2d_2d(h->d_in_i[b], cs * ies, srcI, in_pitch * ies, w_in, h->n_ch, h->s_h2d) ? SDR_ERR_CUDA : 0);
     SDR_TRY(h2d_2d(h->d_in_q[b], cs * ies, srcQ, in_pitch * ies, w_in, h->n_ch, h->s_h2d) ? SDR_ERR_CUDA : 0);
     SDR_TRY(dev_event_record(h->ev_h2d[b], h->s_h2d) ? SDR_ERR_CUDA : 0);
     /* kernel of chunk k: needs its input, and the D2H of chunk k-2 must have drained output set b */
     SDR_TRY(dev_stream_wait(h->s_comp, h->ev_h2d[b]) ? SDR_ERR_CUDA : 0);
-    if (k >= 2) { SDR_TRY(dev_stream_wait(h->s_comp, h->ev_d2h[b]) ? SDR_ERR_CUDA : 0); }
+    if (h->host_seq >= 2) { SDR_TRY(dev_stream_wait(h->s_comp, h->ev_d2h[b]) ? SDR_ERR_CUDA : 0); }
     int rc = sdr_batch_process_device(h, h->d_in_i[b], h->d_in_q[b], cs, in_fmt, h->d_out[b], cs, out_fmt, nb, h->s_comp);
     SDR_TRY(rc);
     SDR_TRY(dev_event_record(h->ev_comp[b], h->s_comp) ? SDR_ERR_CUDA : 0);
@@ -831,11 +849,11 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
     SDR_TRY(dev_stream_wait(h->s_d2h, h->ev_comp[b]) ? SDR_ERR_CUDA : 0);
     SDR_TRY(d2h_2d(dst, out_pitch * oes, h->d_out[b], cs * oes, w_out, h->n_ch, h->s_d2h) ? SDR_ERR_CUDA : 0);
     SDR_TRY(dev_event_record(h->ev_d2h[b], h->s_d2h) ? SDR_ERR_CUDA : 0);
-    done += nb; k++;
+    done += nb; k++; h->host_seq++;
   }
 #undef SDR_TRY
-  if (dev_sync(h->s_d2h) | dev_sync(h->s_comp) | dev_sync(h->s_h2d)) return err ? err : SDR_ERR_CUDA; /* all three are drained either way */
-  return err ? err : SDR_OK;
+  if (err) { dev_sync(h->s_d2h); dev_sync(h->s_comp); dev_sync(h->s_h2d); return err; }
+  return SDR_OK; /* queued: sdr_batch_wait_host() (or any later synchronising call of the handle's streams) completes it */
 }
 
 static int gather_words(sdr_batch_t *h, const uint32_t *ids, uint32_t n, const uint32_t *words, uint32_t nw, std::vector<float> &out) {

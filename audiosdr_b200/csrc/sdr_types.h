@@ -156,7 +156,10 @@ enum { SDRL_CONTRACT = 1u, SDRL_RAW_OUT = 2u };
 
 /* default placement of the stages on the warps of a CTA (warp id % 4 = SM sub-partition, higher id = preferred by the
  * scheduler) for the launches that run all 14 stages; SDR_MAP_SSB / SDR_MAP_ENV (hex) override it for experiments */
-#define SDR_MAP_SSB_DEFAULT 0x3BADC548961720ull
+#define SDR_MAP_SSB_DEFAULT 0xCBA435D8961720ull
+#define SDR_MAP_SSB_NONB_DEFAULT 0xBC84627A3510D9ull /* SSB buckets without the blanker (BASELINE config 5): its three warps idle, so each of three
+                                                         schedulers gets one Hilbert warp and one cascade / the output, the fourth two Hilbert
+                                                         warps (tools/map_search.py --cls ssb --config 5: 1.496 -> 1.257 ms per 128 blocks) */
 #define SDR_MAP_ENV_DEFAULT 0xA0D459B1328C67ull
 #define SDR_MAP_SSB_ALS_DEFAULT 0x4630127BC98DA5ull /* SSB buckets with the ALS filter: its stage (ALS + output) is by far the slowest and wants a
                                                         sub-partition where it wins the scheduler (tools/map_search.py --cls ssb --als) */

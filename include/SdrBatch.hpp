@@ -131,6 +131,12 @@ class SdrBatch {
                     uint32_t n_blocks) {
     check(sdr_batch_process_host(h_, I, Q, in_pitch, in_fmt, audio, out_pitch, out_fmt, n_blocks), "sdr_batch_process_host");
   }
+  /* ... the same as a stream of calls: submit_host() queues and returns, wait_host() completes everything queued */
+  void submit_host(const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio, size_t out_pitch, int out_fmt,
+                   uint32_t n_blocks) {
+    check(sdr_batch_submit_host(h_, I, Q, in_pitch, in_fmt, audio, out_pitch, out_fmt, n_blocks), "sdr_batch_submit_host");
+  }
+  void wait_host() { check(sdr_batch_wait_host(h_), "sdr_batch_wait_host"); }
   sdr_batch_t *handle() { return h_; }
 
  private:

@@ -165,6 +165,16 @@ int sdr_batch_process(sdr_batch_t *h, const float *I, const float *Q, float *aud
 /* Same through HOST buffers (pinned or pageable): H2D copy, kernel, D2H copy, synchronous on return. */
 int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt,
                            void *audio, size_t out_pitch, int out_fmt, uint32_t n_blocks);
+/* The streaming form of the same call (the reference's update() is an endless stream of blocks, C:39-168: one interrupt per
+ * 128 samples): submit_host queues the copies and launches and returns; wait_host returns when everything submitted so far
+ * has landed in the callers' audio buffers.  Calls submitted back to back overlap -- the first copy-in of a call runs beside
+ * the last kernel and copy-out of the call before -- so a stream of calls runs at the speed of the host link, without
+ * the start-up and drain of each call.  Until wait_host returns, the input buffers must stay unchanged and the audio
+ * buffers unread; host buffers must be pinned for the copies to be asynchronous.  Setter calls between two submits take
+ * effect at that block boundary, as everywhere.  process_host == submit_host + wait_host. */
+int sdr_batch_submit_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt,
+                          void *audio, size_t out_pitch, int out_fmt, uint32_t n_blocks);
+int sdr_batch_wait_host(sdr_batch_t *h);
 
 /* Getters for `n` channels (ids == NULL: channels 0..n-1).  Synchronises the handle's last stream. */
 int sdr_batch_get_status(sdr_batch_t *h, const uint32_t *channel_ids, uint32_t n, sdr_channel_status *out);

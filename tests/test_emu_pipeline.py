@@ -407,3 +407,28 @@ def test_emulated_contracting_build_error_profile(oracle, emu_contract_lib, cfg,
     if fin.any():
         scale = max(1.0, float(np.max(np.abs(o2["audio"][fin]))))
         assert float(np.max(np.abs(a2[fin].astype(np.float64) - o2["audio"][fin]))) <= CONTRACT_TOL * scale
+
+
+def test_emulated_host_stream_of_submitted_calls(oracle, emu_lib):
+    """submit_host / wait_host: ragged calls queued back to back (the staging rotation carries over from call to call), a
+    setter between two submits, a synchronous call in between: the oracle's bits."""
+    import audiosdr_b200 as A
+    nblk = 40
+    I, Q, ev = S.make(4, list(range(37)), nblk)
+    ev = [e for e in ev if e[1] == 0] + [(3, 20, "setDemodMode", 2), (9, 20, "setAGCthreshold", -30.0)]
+    o = oracle.run(I, Q, ev, threads=4)
+    out = np.zeros((37, nblk * 128), np.int16)
+    b = A.SdrBatch(37, _lib=emu_lib)
+    b.configure([(None if e[0] == 0xFFFFFFFF else e[0], e[2]) + tuple(e[3:]) for e in ev if e[1] == 0])
+    pos = 0
+    for k, n in enumerate((17, 3, 12, 1, 7)):
+        if pos == 20:
+            b.configure([(3, "setDemodMode", 2), (9, "setAGCthreshold", -30.0)])
+        a, z = pos * 128, (pos + n) * 128
+        if k == 3:
+            b.process_host(I[:, a:z], Q[:, a:z], out[:, a:z])
+        else:
+            b.submit_host(I[:, a:z], Q[:, a:z], out[:, a:z])
+        pos += n
+    b.wait_host()
+    assert np.array_equal(out, o["pcm"])

@@ -349,3 +349,34 @@ def test_cuda_large_single_call(cuda_lib, oracle, dev):
     assert_same(a, o["audio"])
     b = harness.run_batch(cuda_lib, I[:, :60 * 128], Q[:, :60 * 128], ev, chunks=(1,), device=dev)
     assert_same(b, o["audio"][:, :60 * 128])
+
+
+def test_cuda_host_stream_of_submitted_calls(cuda_lib, oracle, dev):
+    """sdr_batch_submit_host / wait_host: a stream of calls queued back to back from pinned host planes (int16 in and out), ragged
+    lengths (odd chunk counts flip the staging rotation), one setter between two submits, one synchronous call in the middle --
+    the audio is the oracle's, bit for bit, once wait_host() has returned."""
+    import torch
+    import audiosdr_b200 as A
+    nblk = 150
+    I, Q, ev = S.make(4, list(range(70)), nblk)
+    ev = [e for e in ev if e[1] == 0] + [(3, 64, "setDemodMode", 2), (40, 64, "setAGCthreshold", -30.0)]
+    o = oracle.run(I, Q, ev, threads=os.cpu_count() or 1)
+    hI, hQ = torch.from_numpy(I).pin_memory(), torch.from_numpy(Q).pin_memory()
+    hO = torch.zeros((70, nblk * 128), dtype=torch.int16).pin_memory()
+    nI, nQ, nO = hI.numpy(), hQ.numpy(), hO.numpy()
+    b = A.SdrBatch(70, _lib=cuda_lib)
+    b.configure([(None if e[0] == 0xFFFFFFFF else e[0], e[2]) + tuple(e[3:]) for e in ev if e[1] == 0])
+    pos = 0
+    for k, n in enumerate((17, 16, 31, 50, 1, 35)):
+        if pos == 64:
+            b.configure([(3, "setDemodMode", 2), (40, "setAGCthreshold", -30.0)])
+        a, z = pos * 128, (pos + n) * 128
+        if k == 4:
+            b.process_host(nI[:, a:z], nQ[:, a:z], nO[:, a:z])  # synchronous call inside the stream
+        else:
+            b.submit_host(nI[:, a:z], nQ[:, a:z], nO[:, a:z])
+        pos += n
+    assert pos == nblk
+    b.wait_host()
+    b.wait_host()  # idempotent
+    assert np.array_equal(nO, o["pcm"]), harness.describe_mismatch(nO.astype(np.float32), o["pcm"].astype(np.float32))
