@@ -152,9 +152,11 @@ struct sdr_batch {
   std::vector<Shadow> sh;
   std::vector<uint32_t> pend_reset; /* per channel SDRK_R_* bits to replay before the next block */
   std::vector<uint32_t> dirty_list;
+  std::vector<uint32_t> cfg_list; std::vector<uint8_t> cfg_mark; bool cfg_all; /* channels whose setters ran since the last sync (cfg_all: every one) */
   bool cfg_dirty, groups_dirty, luts_dirty;
   std::map<AgcKey, int> lut_index;
   std::vector<float> luts; /* [n][SDR_AGC_LUT_STRIDE] */
+  size_t lut_gc_at; /* registry size at which unused tables are looked for next (collect_luts) */
   /* device */
   float *d_state; SdrChanCfg *d_cfg; SdrGroup *d_groups; float *d_luts; SdrTables *d_tabs;
   uint32_t *d_reset_ch, *d_reset_mask; size_t reset_cap; size_t luts_cap; size_t groups_cap;
@@ -290,6 +292,10 @@ int apply_one(sdr_batch *h, uint32_t c, uint32_t op, float a0, float a1, float a
     default: return fail(SDR_ERR_ARG, "unknown setter id");
   }
   h->cfg_dirty = true;
+  if (!h->cfg_all && !h->cfg_mark[c]) {
+    h->cfg_mark[c] = 1; h->cfg_list.push_back(c);
+    if (h->cfg_list.size() > h->n_ch / 4 + 64) { h->cfg_all = true; for (uint32_t k : h->cfg_list) h->cfg_mark[k] = 0; h->cfg_list.clear(); }
+  }
   return 0;
 }
 
@@ -431,7 +437,27 @@ int build_groups(sdr_batch *h) {
 
 int fold_profile(sdr_batch *h);
 
+/* AGC tables nobody uses any more (a sweep of setAGCthreshold / slope / kneeWidth leaves one behind per step): when the
+ * registry has doubled since the last look, keep the tables some channel still points to and renumber them */
+void collect_luts(sdr_batch *h) {
+  const size_t n = h->luts.size() / SDR_AGC_LUT_STRIDE;
+  if (n <= h->lut_gc_at) return;
+  std::vector<int> remap(n, -1);
+  size_t used = 0;
+  for (const Shadow &s : h->sh) if (remap[s.lut_id] < 0) remap[s.lut_id] = (int)used++;
+  if (used < n) {
+    std::vector<float> kept(used * SDR_AGC_LUT_STRIDE);
+    for (size_t i = 0; i < n; i++) if (remap[i] >= 0) memcpy(&kept[(size_t)remap[i] * SDR_AGC_LUT_STRIDE], &h->luts[i * SDR_AGC_LUT_STRIDE], sizeof(float) * SDR_AGC_LUT_STRIDE);
+    h->luts.swap(kept);
+    for (auto it = h->lut_index.begin(); it != h->lut_index.end();) { if (remap[it->second] < 0) it = h->lut_index.erase(it); else { it->second = remap[it->second]; ++it; } }
+    for (Shadow &s : h->sh) s.lut_id = remap[s.lut_id];
+    h->luts_dirty = h->cfg_dirty = h->cfg_all = true;
+  }
+  h->lut_gc_at = std::max<size_t>(64, 2 * used);
+}
+
 int sync_config(sdr_batch *h, void *stream) {
+  collect_luts(h);
   if (h->luts_dirty) {
     size_t need = h->luts.size() * sizeof(float);
     if (need > h->luts_cap) {
@@ -444,10 +470,32 @@ int sync_config(sdr_batch *h, void *stream) {
     h->luts_dirty = false;
   }
   if (h->cfg_dirty) {
-    for (uint32_t c = 0; c < h->n_ch; c++) resolve(h->sh[c], h->h_cfg[c]);
-    if (h2d(h->d_cfg, h->h_cfg.data(), sizeof(SdrChanCfg) * h->n_ch, stream)) return SDR_ERR_CUDA;
+    if (h->cfg_all) {
+      for (uint32_t c = 0; c < h->n_ch; c++) resolve(h->sh[c], h->h_cfg[c]);
+      if (h2d(h->d_cfg, h->h_cfg.data(), sizeof(SdrChanCfg) * h->n_ch, stream)) return SDR_ERR_CUDA;
+      h->groups_dirty = true; /* group feature summaries depend on the flags */
+    } else {
+      /* only the channels whose setters ran: re-resolve them, upload the span they cover (or each one, when they are few
+       * and far apart), and plan the groups again only if something the grouping depends on has changed */
+      uint32_t lo = h->n_ch, hi = 0;
+      for (uint32_t c : h->cfg_list) {
+        const SdrChanCfg old = h->h_cfg[c];
+        resolve(h->sh[c], h->h_cfg[c]);
+        const SdrChanCfg &now = h->h_cfg[c];
+        if (old.mode != now.mode || old.flags != now.flags || old.agc_lut != now.agc_lut || old.als_m != now.als_m || old.als_delay != now.als_delay)
+          h->groups_dirty = true;
+        lo = std::min(lo, c); hi = std::max(hi, c);
+        h->cfg_mark[c] = 0;
+      }
+      if (!h->cfg_list.empty()) {
+        if (h->cfg_list.size() <= 16 && (size_t)(hi - lo + 1) > 64 * h->cfg_list.size()) {
+          for (uint32_t c : h->cfg_list) if (h2d(h->d_cfg + c, &h->h_cfg[c], sizeof(SdrChanCfg), stream)) return SDR_ERR_CUDA;
+        } else if (h2d(h->d_cfg + lo, &h->h_cfg[lo], sizeof(SdrChanCfg) * (hi - lo + 1), stream)) return SDR_ERR_CUDA;
+      }
+    }
+    for (uint32_t c : h->cfg_list) h->cfg_mark[c] = 0; /* (also when cfg_all was raised with channels already listed) */
+    h->cfg_list.clear(); h->cfg_all = false;
     h->cfg_dirty = false;
-    h->groups_dirty = true; /* group feature summaries depend on the flags */
   }
   if (h->groups_dirty) {
     if (h->prof_on && fold_profile(h)) return SDR_ERR_CUDA; /* rows are per group: fold before the grouping changes */
@@ -570,8 +618,8 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   sdr_batch *h = new sdr_batch();
   h->desc = *desc; h->n_ch = desc->n_channels;
   h->ch_stride = ((size_t)h->n_ch + 31) / 32 * 32;
-  h->sh.resize(h->n_ch); h->pend_reset.assign(h->n_ch, 0); h->h_cfg.resize(h->n_ch);
-  h->cfg_dirty = h->groups_dirty = true; h->luts_dirty = false;
+  h->sh.resize(h->n_ch); h->pend_reset.assign(h->n_ch, 0); h->h_cfg.resize(h->n_ch); h->cfg_mark.assign(h->n_ch, 0);
+  h->cfg_dirty = h->groups_dirty = true; h->luts_dirty = false; h->cfg_all = true; h->lut_gc_at = 64;
   h->d_state = nullptr; h->d_cfg = nullptr; h->d_groups = nullptr; h->d_luts = nullptr; h->d_tabs = nullptr;
   h->d_reset_ch = h->d_reset_mask = nullptr; h->reset_cap = h->luts_cap = h->groups_cap = 0;
   h->d_gather = nullptr; h->d_gather_ids = h->d_gather_words = nullptr; h->gather_cap = 0;
@@ -986,7 +1034,7 @@ int sdr_batch_import_state(sdr_batch_t *h, const uint32_t *ids, uint32_t n, cons
     memcpy(w, b + wo, sizeof(float) * SDR_STATE_WORDS);
     rotate_slots(w, (uint32_t)((h->blocks_done % 3) + 3 - hd.phase));
   }
-  h->cfg_dirty = true; h->groups_dirty = true;
+  h->cfg_dirty = true; h->groups_dirty = true; h->cfg_all = true; /* (the shadows were written directly) */
   void *s = h->last_stream;
   float *d_in = nullptr; uint32_t *d_ids = nullptr;
   do {

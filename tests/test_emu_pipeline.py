@@ -432,3 +432,27 @@ def test_emulated_host_stream_of_submitted_calls(oracle, emu_lib):
         pos += n
     b.wait_host()
     assert np.array_equal(out, o["pcm"])
+
+
+def test_emulated_agc_parameter_sweep_collects_tables(oracle, emu_lib):
+    """A setter sweep (one new AGC table per block on two channels, 150 of them) crosses the point where the host drops the
+    tables nobody uses any more and renumbers the rest; setters on single channels take the incremental upload path."""
+    nblk = 150
+    I, Q, ev = S.make(4, list(range(40)), nblk)
+    ev = [e for e in ev if e[1] == 0]
+    for k in range(1, nblk):
+        ev.append((2, k, "setAGCthreshold", -10.0 - 0.25 * k))
+        if k % 2:
+            ev.append((33, k, "setAGCslope", 2.0 + 0.05 * k))
+        if k % 17 == 0:
+            ev.append((5, k, "setOutputGain", 0.1 + 0.01 * k))
+    o = oracle.run(I, Q, ev, threads=4)
+    a, b = harness.run_batch(emu_lib, I, Q, ev, chunks=(1, 3, 2), return_batch=True)
+    assert harness.bits_equal(a, o["audio"]), harness.describe_mismatch(a, o["audio"])
+    # the getters still find every channel's own table after the renumbering: same table as a fresh handle set to the final values
+    import audiosdr_b200 as A
+    f = A.SdrBatch(40, _lib=emu_lib)
+    f.configure([(None if e[0] == 0xFFFFFFFF else e[0], e[2]) + tuple(e[3:]) for e in ev if e[1] == 0])
+    f.configure([(2, "setAGCthreshold", -10.0 - 0.25 * (nblk - 1)), (33, "setAGCslope", 2.0 + 0.05 * (nblk - 1))])
+    for c in (0, 2, 33, 39):
+        assert np.array_equal(b.getAGClookup(c), f.getAGClookup(c))
