@@ -806,15 +806,23 @@ int sdr_batch_wait_host(sdr_batch_t *h) {
   return SDR_OK;
 }
 
+static int host_call(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio, size_t out_pitch, int out_fmt,
+                     uint32_t n_blocks, bool streamed);
+
 int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio,
                            size_t out_pitch, int out_fmt, uint32_t n_blocks) {
-  const int rc = sdr_batch_submit_host(h, I, Q, in_pitch, in_fmt, audio, out_pitch, out_fmt, n_blocks);
-  if (rc) return rc; /* (submit has drained the streams) */
+  const int rc = host_call(h, I, Q, in_pitch, in_fmt, audio, out_pitch, out_fmt, n_blocks, false);
+  if (rc) return rc; /* (the streams have been drained) */
   return sdr_batch_wait_host(h);
 }
 
 int sdr_batch_submit_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio,
                           size_t out_pitch, int out_fmt, uint32_t n_blocks) {
+  return host_call(h, I, Q, in_pitch, in_fmt, audio, out_pitch, out_fmt, n_blocks, true);
+}
+
+static int host_call(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio, size_t out_pitch, int out_fmt,
+                     uint32_t n_blocks, bool streamed) {
   if (!h || !I || !Q || !audio) return fail(SDR_ERR_ARG, "process_host: bad arguments");
   if (n_blocks == 0) return fail(SDR_ERR_ARG, "n_blocks == 0");
   if (in_fmt != SDR_FMT_I16 && in_fmt != SDR_FMT_F32) return fail(SDR_ERR_ARG, "process_host: unknown input format");
@@ -824,8 +832,12 @@ int sdr_batch_submit_host(sdr_batch_t *h, const void *I, const void *Q, size_t i
   const size_t ies = in_fmt == SDR_FMT_F32 ? 4 : 2, oes = out_fmt == SDR_FMT_F32 ? 4 : 2;
   if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
   /* chunking along time: ~12 chunks per call, at least 16 blocks each (every chunk is one kernel launch that
-   * reloads and saves the per-channel state, so chunks should not be tiny) */
-  static const uint32_t want_chunks = []() { const char *e = getenv("SDR_HOST_CHUNKS"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 12); }();
+   * reloads and saves the per-channel state, so chunks should not be tiny).  A synchronous call wants many chunks: its first
+   * copy-in and its last kernel + copy-out are exposed.  A streamed call hides both behind its neighbours and wants the
+   * rows of its strided copies long instead: 6 chunks (measured on config 2, streamed / synchronous Msps: 2 chunks 11.5 / 9.0,
+   * 4: 12.0 / 10.5, 6: 12.3 / 11.0, 8: 11.9 / 11.1, 12: 12.0 / 11.4, 16: 10.9 / 10.6, 24: 10.6 / 10.5; run r02u). */
+  static const uint32_t env_chunks = []() { const char *e = getenv("SDR_HOST_CHUNKS"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 0); }();
+  const uint32_t want_chunks = env_chunks ? env_chunks : (streamed ? 6u : 12u);
   static const uint32_t min_chunk = []() { const char *e = getenv("SDR_HOST_MIN_CHUNK"); int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 16); }();
   static const uint32_t ramp = []() { const char *e = getenv("SDR_HOST_RAMP"); int v = e ? atoi(e) : -1; return (uint32_t)(v >= 0 ? v : 0); }();
   uint32_t chunk = (n_blocks + want_chunks - 1) / want_chunks;

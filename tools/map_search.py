@@ -18,6 +18,7 @@ ap.add_argument("--seconds", type=float, default=150.0)
 ap.add_argument("--blocks", type=int, default=128)
 ap.add_argument("--start", default="")
 ap.add_argument("--als", action="store_true", help="enable the ALS filter on every channel (the placement of buckets with ALS)")
+ap.add_argument("--idle", default="", help="hex digits of stages that idle in this bucket (config 5: 1CD = blanker scan, envelope, blanker out): placements that differ only in them count as one")
 ap.add_argument("--config", type=int, default=0, help="BASELINE config to take signals and setters from (default: 2 for ssb, 3 for env)")
 args = ap.parse_args()
 cfg_id = args.config or (2 if args.cls == "ssb" else 3)
@@ -52,8 +53,9 @@ def measure(perm, reps=3):
         best = min(best, e0.elapsed_time(e1))
     return best
 
-def canon(perm):  # the four Hilbert warps (SSB stages 5..8) are interchangeable
-    return tuple(5 if (args.cls == "ssb" and 5 <= s <= 8) else s for s in perm)
+IDLE = set(int(c, 16) for c in args.idle)
+def canon(perm):  # the four Hilbert warps (SSB stages 5..8) are interchangeable, and so are stages that idle
+    return tuple(5 if (args.cls == "ssb" and 5 <= s <= 8) else (99 if s in IDLE else s) for s in perm)
 
 if args.cls == "envmerged":
     start = [int(c) for c in args.start] if args.start else [1, 2, 0, 5, 4, 6, 3]
