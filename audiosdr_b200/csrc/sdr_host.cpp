@@ -352,7 +352,7 @@ int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm, uint32_t handle_gro
   /* measured placements */
   if (b.lay.n_warps == SDR_STAGES) {
     unsigned long long m = cls == CLS_SSB ? ((feat & LF_ALS) ? SDR_MAP_SSB_ALS_DEFAULT : (feat & LF_NB) ? SDR_MAP_SSB_DEFAULT : SDR_MAP_SSB_NONB_DEFAULT)
-                                          : SDR_MAP_ENV_DEFAULT;
+                                          : ((feat & LF_NB) && !(feat & LF_ALS) ? SDR_MAP_ENV_NB_DEFAULT : SDR_MAP_ENV_DEFAULT);
     if (const char *e = getenv(cls == CLS_SSB ? "SDR_MAP_SSB" : "SDR_MAP_ENV")) m = strtoull(e, nullptr, 16);
     lay_place(&b.lay, m);
   } else if (cls == CLS_ENV && b.lay.n_warps == 11) {

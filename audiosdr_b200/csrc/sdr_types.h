@@ -161,6 +161,8 @@ enum { SDRL_CONTRACT = 1u, SDRL_RAW_OUT = 2u };
                                                          schedulers gets one Hilbert warp and one cascade / the output, the fourth two Hilbert
                                                          warps (tools/map_search.py --cls ssb --config 5: 1.496 -> 1.257 ms per 128 blocks) */
 #define SDR_MAP_ENV_DEFAULT 0xA0D459B1328C67ull
+#define SDR_MAP_ENV_NB_DEFAULT 0x19430DB7A258C6ull /* ENV buckets with the blanker (BASELINE config 4's AM and SAM buckets; its three warps work
+                                                       there): tools/map_search.py --cls env --config 4 --split, 4.019 -> 3.685 ms per 64 blocks */
 #define SDR_MAP_SSB_ALS_DEFAULT 0x4630127BC98DA5ull /* SSB buckets with the ALS filter: its stage (ALS + output) is by far the slowest and wants a
                                                         sub-partition where it wins the scheduler (tools/map_search.py --cls ssb --als) */
 #define SDR_MAP_ENV_LEAN_DEFAULT 0x52980364BA7ull /* the 11-warp ENV plan on 16-sample tiles, two groups per SM (tools/map_search.py --cls envlean) */

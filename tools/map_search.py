@@ -18,6 +18,9 @@ ap.add_argument("--seconds", type=float, default=150.0)
 ap.add_argument("--blocks", type=int, default=128)
 ap.add_argument("--start", default="")
 ap.add_argument("--als", action="store_true", help="enable the ALS filter on every channel (the placement of buckets with ALS)")
+ap.add_argument("--nb", action="store_true", help="enable the noise blanker on every channel (ENV buckets with blanker: BASELINE config 4's)")
+ap.add_argument("--mode", type=int, default=-1, help="setDemodMode(mode) on every channel after the config's own setters (4 = AM, 5 = SAM)")
+ap.add_argument("--split", action="store_true", help="force the two-launch form of ALS buckets (SDR_ALS_SPLIT=1): with --config 4 the ENV chain launches of BASELINE config 4 (blanker on, ALS in the post-pass)")
 ap.add_argument("--idle", default="", help="hex digits of stages that idle in this bucket (config 5: 1CD = blanker scan, envelope, blanker out): placements that differ only in them count as one")
 ap.add_argument("--config", type=int, default=0, help="BASELINE config to take signals and setters from (default: 2 for ssb, 3 for env)")
 args = ap.parse_args()
@@ -25,6 +28,8 @@ cfg_id = args.config or (2 if args.cls == "ssb" else 3)
 nch = 4096 if args.cls not in ("envlean", "envmerged") else 16384   # enough groups for the plans that share an SM (sdr_host.cpp, plan_bucket)
 if args.cls == "envlean":
     os.environ["SDR_NO_MERGE"] = "1"; os.environ["SDR_TILE_ENV"] = "16"; os.environ["SDR_CTAS_PER_SM"] = "2"
+if args.split:
+    os.environ["SDR_ALS_SPLIT"] = "1"
 os.environ["SDR_MAP_SEARCH"] = "1"               # the host re-plans at every call, so that it reads the placement variable again
 dev = torch.device("cuda:0")
 I16, Q16, calls = bench.synth_planes(dev, 0, nch, args.blocks * 128, 1234, cfg_id)
@@ -34,6 +39,10 @@ b = api.SdrBatch(nch)
 b.configure(calls)
 if args.als:
     b.enableALSfilter(None)
+if args.mode >= 0:
+    b.setDemodMode(None, args.mode)
+if args.nb:
+    b.enableNoiseBlanker(None)
 var = {"ssb": "SDR_MAP_SSB", "env": "SDR_MAP_ENV", "envlean": "SDR_MAP_ENV_LEAN", "envmerged": "SDR_MAP_ENV_MERGED"}[args.cls]
 NW = {"envlean": 11, "envmerged": 7}.get(args.cls, 14)
 stream = torch.cuda.current_stream()
