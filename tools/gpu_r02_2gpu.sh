@@ -1,9 +1,8 @@
 #!/bin/bash
-# tools/gpu_r02_2gpu.sh -- two ranks under torchrun: the bench line (all workloads, config 3 strong-scaled), the reference arm, GPU tests.
+# tools/gpu_r02_2gpu.sh -- two ranks under torchrun: the bench line (all workloads, config 3 strong-scaled) and the reference arm.
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r02_2gpu}
-echo "== pytest gpu (merged-plan change)"; timeout 900 python -m pytest tests -m gpu -x -q -k "short_tile or sam_driven or per_config or smoke" > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest_gpu.log
 echo "== bench, 2 ranks"; ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ) 2>&1 | grep real; tail -4 gpurun_out/${TAG}_bench.err | cut -c1-300
 python - <<PY
 import json
