@@ -458,6 +458,7 @@ def main():
                     help="diagnostics only: make BASELINE config 3 / 4 / 5 the line's workload instead of the headline config 2")
     ap.add_argument("--only-headline", action="store_true", help="skip the config 3 / 4 / 5 workloads and the sustained run")
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
+    ap.add_argument("--no-aux", action="store_true", help="skip the bench_aux.py summary (aux_blocks)")
     ap.add_argument("--variant", default="", help="diagnostics only: comma list of nonb,noagc,noaud,als (changes the workload!)")
     ap.add_argument("--role-profile", action="store_true", help="per-stage busy fractions (adds clock reads; not for headline numbers)")
     ap.add_argument("--contract", action="store_true", help="diagnostics only: the opt-in contracting build (not bit-exact) as the line's workload")
@@ -623,6 +624,24 @@ def main():
             except Exception as e:  # a side workload must not take the headline line down with it
                 workloads["config%d" % other] = dict(error="%s: %s" % (type(e).__name__, e))
 
+    # ---- the blocks either side of the chain (I/Q generator, pre-processor, grabber spectrum tap), measured by
+    # bench_aux.py in a process of its own and summarised here so that the one line the driver keeps carries them
+    aux_blocks = None
+    if rank == 0 and world == 1 and not diagnostic and not args.only_headline and not args.no_aux:
+        aux_blocks = {}
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench_aux.py"), "--no-cpu-baseline", "--steps", "5", "--warmup", "3", "--e2e-steps", "1"],
+                               capture_output=True, text=True, timeout=240)
+            for ln in r.stdout.splitlines():
+                if not ln.startswith("{"):
+                    continue
+                a = json.loads(ln)
+                aux_blocks[a.get("path", "?")] = {k: a.get(k) for k in ("value", "unit", "ms_per_step", "parity", "roofline", "roofline_fp32_issue", "spectra_per_s", "e2e", "gpu_launches") if a.get(k) is not None}
+            if not aux_blocks:
+                aux_blocks = dict(error=(r.stderr or "no output")[-300:])
+        except Exception as e:
+            aux_blocks = dict(error="%s: %s" % (type(e).__name__, e))
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_rate(args.cpu_seconds, os.cpu_count() or 1)
@@ -636,6 +655,7 @@ def main():
                     role_profile=role_profile, variant=args.variant or None,
                     diagnostic_workload=(None if cfg_id == CONFIG_ID else "BASELINE configs[%d], %d channels/GPU: NOT the headline metric" % (cfg_id - 1, nch)),
                     parity=parity, status=status, host_affinity=affinity, sustained=sustained, contracting_build=contracting, workloads=workloads,
+                    aux_blocks=aux_blocks,
                     per_launch_ms=dict(mean=float(np.mean(per_launch_ms)), min=float(np.min(per_launch_ms)), max=float(np.max(per_launch_ms))))
         print(json.dumps(line), flush=True)
     if world > 1:
