@@ -853,18 +853,21 @@ static int host_call(sdr_batch_t *h, const void *I, const void *Q, size_t in_pit
   }
   if (in_bytes > h->stage_in_bytes || out_bytes > h->stage_out_bytes) {
     dev_sync(h->last_stream); dev_sync(h->s_h2d); dev_sync(h->s_comp); dev_sync(h->s_d2h);
+    const bool grow_in = in_bytes > h->stage_in_bytes, grow_out = out_bytes > h->stage_out_bytes;
+    if (grow_in) h->stage_in_bytes = 0; /* (an allocation that fails below leaves no stale size behind: the next call allocates again) */
+    if (grow_out) h->stage_out_bytes = 0;
     for (int k = 0; k < 2; k++) {
-      if (in_bytes > h->stage_in_bytes) {
+      if (grow_in) {
         dev_free(h->d_in_i[k]); dev_free(h->d_in_q[k]); h->d_in_i[k] = h->d_in_q[k] = nullptr;
         if (dev_alloc(&h->d_in_i[k], in_bytes) || dev_alloc(&h->d_in_q[k], in_bytes)) return SDR_ERR_NOMEM;
       }
-      if (out_bytes > h->stage_out_bytes) {
+      if (grow_out) {
         dev_free(h->d_out[k]); h->d_out[k] = nullptr;
         if (dev_alloc(&h->d_out[k], out_bytes)) return SDR_ERR_NOMEM;
       }
     }
-    if (in_bytes > h->stage_in_bytes) h->stage_in_bytes = in_bytes;
-    if (out_bytes > h->stage_out_bytes) h->stage_out_bytes = out_bytes;
+    if (grow_in) h->stage_in_bytes = in_bytes;
+    if (grow_out) h->stage_out_bytes = out_bytes;
   }
   /* work queued by an earlier process_device call on another stream must finish before the state is touched here */
   if (h->last_stream != h->s_comp && dev_sync(h->last_stream)) return SDR_ERR_CUDA;
