@@ -356,7 +356,9 @@ class Workload:
         w = WORKLOADS[cfg_id]
         self.cfg_id, self.rank, self.world, self.dev = cfg_id, rank, world, dev
         if w["scaling"] == "strong":
-            self.first, end = shard_range(w["channels"], rank, world); self.nch = end - self.first
+            # diagnostics: SDR_BENCH_WORLD=n on one GPU measures the shard rank 0 of n ranks would get (plan choice per shard size)
+            emu_world = int(os.environ.get("SDR_BENCH_WORLD", "0") or 0)
+            self.first, end = shard_range(w["channels"], rank, emu_world if (emu_world > 0 and world == 1) else world); self.nch = end - self.first
         else:
             self.nch = w["channels"]; self.first = rank * self.nch
         self.nblk = nblk or w["blocks"]; self.ns = self.nblk * 128
