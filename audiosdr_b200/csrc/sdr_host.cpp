@@ -329,7 +329,11 @@ int plan_bucket(Bucket &b, int cls, uint32_t feat, int n_sm, uint32_t handle_gro
   const bool lean = !(feat & (LF_NB | LF_ALS));
   if (cls == CLS_ENV && lean && b.count > (uint32_t)n_sm) {
     if ((feat & LF_SAM) && b.count > 2u * (uint32_t)n_sm) { T = 16; ctas = 3; in_depth = 1; } /* 76.7 KB: three fit an SM exactly */
-    else { T = 16; ctas = 2; }
+    else {
+      /* at most two groups per SM: the 11-warp plan spreads a group over more warps than the merged one and is the faster of
+       * the two while the SM is not crowded (8 192 SAM channels = the shard of one of eight GPUs: 40.6 against 37.3 G, run r02z) */
+      T = 16; ctas = 2; feat &= ~(uint32_t)LF_SAM;
+    }
   }
   const int t_env = env_int(cls == CLS_SSB ? "SDR_TILE_SSB" : "SDR_TILE_ENV", 0);
   if (t_env && lean) { T = t_env; ctas = T == 32 ? 1 : 2; in_depth = 0; }
