@@ -30,7 +30,7 @@ EXPORTS = ["sdr_batch_create", "sdr_batch_destroy", "sdr_batch_set", "sdr_batch_
            "sdr_batch_process_host", "sdr_batch_get_status", "sdr_batch_get_agc_lookup", "sdr_batch_peek_state",
            "sdr_batch_get_role_profile", "sdr_batch_launch_count", "sdr_batch_last_error", "sdr_batch_version",
            "sdr_batch_process", "sdr_batch_state_bytes", "sdr_batch_export_state", "sdr_batch_import_state",
-           "sdr_batch_submit_host", "sdr_batch_wait_host"]
+           "sdr_batch_submit_host", "sdr_batch_wait_host", "sdr_batch_host_ticket", "sdr_batch_wait_host_ticket"]
 
 
 class SdrError(RuntimeError):
@@ -73,6 +73,9 @@ def _bind(L):
                                          C.c_size_t, C.c_int, C.c_uint32]
     L.sdr_batch_submit_host.argtypes = L.sdr_batch_process_host.argtypes
     L.sdr_batch_wait_host.argtypes = [C.c_void_p]
+    L.sdr_batch_host_ticket.argtypes = [C.c_void_p]
+    L.sdr_batch_host_ticket.restype = C.c_uint64
+    L.sdr_batch_wait_host_ticket.argtypes = [C.c_void_p, C.c_uint64]
     L.sdr_batch_get_status.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_get_agc_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdr_batch_peek_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
@@ -287,6 +290,11 @@ class SdrBatch:
         self._check(self.L.sdr_batch_submit_host(self.h, I.ctypes.data, Q.ctypes.data, I.strides[0] // I.itemsize,
                                                  _fmt_of(str(I.dtype)), audio.ctypes.data,
                                                  audio.strides[0] // audio.itemsize, _fmt_of(str(audio.dtype)), n_blocks))
+        return int(self.L.sdr_batch_host_ticket(self.h))
 
-    def wait_host(self):
-        self._check(self.L.sdr_batch_wait_host(self.h))
+    def wait_host(self, ticket=None):
+        """Everything submitted so far (ticket None), or the call `submit_host` returned `ticket` for (later calls stay in flight)."""
+        if ticket is None:
+            self._check(self.L.sdr_batch_wait_host(self.h))
+        else:
+            self._check(self.L.sdr_batch_wait_host_ticket(self.h, int(ticket)))

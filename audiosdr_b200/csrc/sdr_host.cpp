@@ -64,6 +64,7 @@ int dev_event_create(void **e) { cudaEvent_t t; CU(cudaEventCreateWithFlags(&t, 
 void dev_event_destroy(void *e) { if (e) cudaEventDestroy((cudaEvent_t)e); }
 int dev_event_record(void *e, void *s) { CU(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return 0; }
 int dev_stream_wait(void *s, void *e) { CU(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0)); return 0; }
+int dev_event_sync(void *e) { CU(cudaEventSynchronize((cudaEvent_t)e)); return 0; }
 #else
 int dev_alloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : fail(SDR_ERR_NOMEM, "calloc"); }
 void dev_free(void *p) { free(p); }
@@ -84,6 +85,7 @@ int dev_event_create(void **e) { *e = nullptr; return 0; }
 void dev_event_destroy(void *) {}
 int dev_event_record(void *, void *) { return 0; }
 int dev_stream_wait(void *, void *) { return 0; }
+int dev_event_sync(void *) { return 0; }
 #endif
 
 inline float tabf(const uint32_t *t, int i) { float f; memcpy(&f, &t[i], 4); return f; }
@@ -142,6 +144,7 @@ struct Bucket {
   bool split; SdrLay lay_main, lay_als;
 };
 
+enum { SDR_HOST_TICKETS = 8 }; /* host calls whose completion can be waited for one by one (sdr_batch_wait_host_ticket) */
 enum { SDR_MAX_BUCKETS = 12 }; /* SSB class: blanker x ALS = 4; ENV class: blanker x ALS x SAM-only = 8 */
 
 struct sdr_batch {
@@ -166,6 +169,7 @@ struct sdr_batch {
   void *d_in_i[2], *d_in_q[2], *d_out[2]; size_t stage_in_bytes, stage_out_bytes;
   void *s_h2d, *s_comp, *s_d2h; void *ev_h2d[2], *ev_comp[2], *ev_d2h[2];
   uint64_t host_seq; /* chunks queued by submit_host since create: chunk n uses staging set n & 1 */
+  uint64_t host_calls; void *ev_call[SDR_HOST_TICKETS]; /* host calls queued since create (= the ticket of the latest); call t's last copy-out records ev_call[t % SDR_HOST_TICKETS] */
   uint32_t n_groups;
   float *d_raw[SDR_MAX_BUCKETS]; size_t raw_cap[SDR_MAX_BUCKETS]; /* scratch planes of split ALS buckets (by bucket index), grown on demand */
   unsigned long long *d_prof; size_t prof_cap; bool prof_on; uint64_t prof_launches;
@@ -608,6 +612,7 @@ void sdr_batch_destroy(sdr_batch_t *h) {
     dev_event_destroy(h->ev_h2d[k]); dev_event_destroy(h->ev_comp[k]); dev_event_destroy(h->ev_d2h[k]);
   }
   dev_stream_destroy(h->s_h2d); dev_stream_destroy(h->s_comp); dev_stream_destroy(h->s_d2h);
+  for (int k = 0; k < SDR_HOST_TICKETS; k++) dev_event_destroy(h->ev_call[k]);
   for (int k = 0; k < SDR_MAX_BUCKETS; k++) { if (h->s_aux[k]) dev_sync(h->s_aux[k]); dev_stream_destroy(h->s_aux[k]); dev_event_destroy(h->ev_join[k]); }
   dev_event_destroy(h->ev_fork);
   dev_free(h->d_prof);
@@ -629,6 +634,7 @@ int sdr_batch_create(sdr_batch_t **out, const sdr_batch_desc *desc) {
   h->d_gather = nullptr; h->d_gather_ids = h->d_gather_words = nullptr; h->gather_cap = 0;
   for (int k = 0; k < 2; k++) { h->d_in_i[k] = h->d_in_q[k] = h->d_out[k] = nullptr; h->ev_h2d[k] = h->ev_comp[k] = h->ev_d2h[k] = nullptr; }
   h->s_h2d = h->s_comp = h->s_d2h = nullptr; h->stage_in_bytes = h->stage_out_bytes = 0; h->host_seq = 0;
+  h->host_calls = 0; for (int k = 0; k < SDR_HOST_TICKETS; k++) h->ev_call[k] = nullptr;
   h->n_groups = 0; h->blocks_done = 0; h->launches = 0; h->last_stream = nullptr;
   h->d_prof = nullptr; h->prof_cap = 0; h->prof_launches = 0;
   for (int k = 0; k < SDR_MAX_BUCKETS; k++) { h->d_raw[k] = nullptr; h->raw_cap[k] = 0; }
@@ -810,6 +816,19 @@ int sdr_batch_wait_host(sdr_batch_t *h) {
   return SDR_OK;
 }
 
+uint64_t sdr_batch_host_ticket(const sdr_batch_t *h) { return h ? h->host_calls : 0; }
+
+int sdr_batch_wait_host_ticket(sdr_batch_t *h, uint64_t ticket) {
+  if (!h) return fail(SDR_ERR_ARG, "wait_host_ticket: bad arguments");
+  if (ticket > h->host_calls) return fail(SDR_ERR_ARG, "wait_host_ticket: no such call yet");
+  if (ticket == 0 || !h->s_comp) return SDR_OK;
+  if (dev_select(h->desc.device)) return SDR_ERR_CUDA;
+  /* copy-outs complete in the order of the calls: a ticket whose event has been reused is covered by the oldest one still kept */
+  const uint64_t oldest = h->host_calls >= SDR_HOST_TICKETS ? h->host_calls - SDR_HOST_TICKETS + 1 : 1;
+  const uint64_t t = ticket < oldest ? oldest : ticket;
+  return dev_event_sync(h->ev_call[t % SDR_HOST_TICKETS]) ? SDR_ERR_CUDA : SDR_OK;
+}
+
 static int host_call(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt, void *audio, size_t out_pitch, int out_fmt,
                      uint32_t n_blocks, bool streamed);
 
@@ -854,6 +873,7 @@ static int host_call(sdr_batch_t *h, const void *I, const void *Q, size_t in_pit
     if (dev_stream_create(&h->s_h2d) || dev_stream_create(&h->s_comp) || dev_stream_create(&h->s_d2h)) return SDR_ERR_CUDA;
     for (int k = 0; k < 2; k++)
       if (dev_event_create(&h->ev_h2d[k]) || dev_event_create(&h->ev_comp[k]) || dev_event_create(&h->ev_d2h[k])) return SDR_ERR_CUDA;
+    for (int k = 0; k < SDR_HOST_TICKETS; k++) if (dev_event_create(&h->ev_call[k])) return SDR_ERR_CUDA;
   }
   if (in_bytes > h->stage_in_bytes || out_bytes > h->stage_out_bytes) {
     dev_sync(h->last_stream); dev_sync(h->s_h2d); dev_sync(h->s_comp); dev_sync(h->s_d2h);
@@ -920,7 +940,10 @@ static int host_call(sdr_batch_t *h, const void *I, const void *Q, size_t in_pit
   }
 #undef SDR_TRY
   if (err) { dev_sync(h->s_d2h); dev_sync(h->s_comp); dev_sync(h->s_h2d); return err; }
-  return SDR_OK; /* queued: sdr_batch_wait_host() (or any later synchronising call of the handle's streams) completes it */
+  /* the call's ticket: its last copy-out is the last thing in the copy-out stream */
+  h->host_calls++;
+  if (dev_event_record(h->ev_call[h->host_calls % SDR_HOST_TICKETS], h->s_d2h)) return SDR_ERR_CUDA;
+  return SDR_OK; /* queued: sdr_batch_wait_host() / sdr_batch_wait_host_ticket() complete it */
 }
 
 static int gather_words(sdr_batch_t *h, const uint32_t *ids, uint32_t n, const uint32_t *words, uint32_t nw, std::vector<float> &out) {

@@ -137,6 +137,8 @@ class SdrBatch {
     check(sdr_batch_submit_host(h_, I, Q, in_pitch, in_fmt, audio, out_pitch, out_fmt, n_blocks), "sdr_batch_submit_host");
   }
   void wait_host() { check(sdr_batch_wait_host(h_), "sdr_batch_wait_host"); }
+  uint64_t host_ticket() const { return sdr_batch_host_ticket(h_); } /* names the call submitted last */
+  void wait_host(uint64_t ticket) { check(sdr_batch_wait_host_ticket(h_, ticket), "sdr_batch_wait_host_ticket"); }
   sdr_batch_t *handle() { return h_; }
 
  private:

@@ -175,6 +175,11 @@ int sdr_batch_process_host(sdr_batch_t *h, const void *I, const void *Q, size_t 
 int sdr_batch_submit_host(sdr_batch_t *h, const void *I, const void *Q, size_t in_pitch, int in_fmt,
                           void *audio, size_t out_pitch, int out_fmt, uint32_t n_blocks);
 int sdr_batch_wait_host(sdr_batch_t *h);
+/* One call at a time: sdr_batch_host_ticket() right after a submit_host (or process_host) names that call (1, 2, ...);
+ * wait_host_ticket returns when that call's audio has landed, while later calls stay in flight -- a receiver that keeps
+ * two calls queued drains call n while call n + 1 is being copied in and computed.  Calls complete in order. */
+uint64_t sdr_batch_host_ticket(const sdr_batch_t *h);
+int sdr_batch_wait_host_ticket(sdr_batch_t *h, uint64_t ticket);
 
 /* Getters for `n` channels (ids == NULL: channels 0..n-1).  Synchronises the handle's last stream. */
 int sdr_batch_get_status(sdr_batch_t *h, const uint32_t *channel_ids, uint32_t n, sdr_channel_status *out);

@@ -428,10 +428,13 @@ def test_emulated_host_stream_of_submitted_calls(oracle, emu_lib):
         if k == 3:
             b.process_host(I[:, a:z], Q[:, a:z], out[:, a:z])
         else:
-            b.submit_host(I[:, a:z], Q[:, a:z], out[:, a:z])
+            assert b.submit_host(I[:, a:z], Q[:, a:z], out[:, a:z]) == k + 1  # the call's ticket
         pos += n
+    b.wait_host(ticket=2)
     b.wait_host()
     assert np.array_equal(out, o["pcm"])
+    with pytest.raises(A.SdrError):
+        b.wait_host(ticket=99)
 
 
 def test_emulated_agc_parameter_sweep_collects_tables(oracle, emu_lib):

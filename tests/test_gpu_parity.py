@@ -374,9 +374,17 @@ def test_cuda_host_stream_of_submitted_calls(cuda_lib, oracle, dev):
         if k == 4:
             b.process_host(nI[:, a:z], nQ[:, a:z], nO[:, a:z])  # synchronous call inside the stream
         else:
-            b.submit_host(nI[:, a:z], nQ[:, a:z], nO[:, a:z])
+            t = b.submit_host(nI[:, a:z], nQ[:, a:z], nO[:, a:z])
+            assert t == k + 1  # tickets count the host calls of the handle, synchronous ones included
+        if k == 2:  # one call at a time: the first call's audio is there while the third may still be in flight
+            b.wait_host(ticket=1)
+            assert np.array_equal(nO[:, :17 * 128], o["pcm"][:, :17 * 128])
         pos += n
     assert pos == nblk
+    b.wait_host(ticket=6)
+    assert np.array_equal(nO, o["pcm"])
     b.wait_host()
     b.wait_host()  # idempotent
+    with pytest.raises(A.SdrError):
+        b.wait_host(ticket=7)  # no such call yet
     assert np.array_equal(nO, o["pcm"]), harness.describe_mismatch(nO.astype(np.float32), o["pcm"].astype(np.float32))
